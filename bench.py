@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- APPNP K=10 propagation on the ogbn-products-shaped synthetic graph
+(BASELINE.json configs[3], the configuration the metric "GCN/APPNP propagate GTEPS & HBM GB/s vs
+peak ... at 1/2/4/8 GPU" is quoted on; it fits one GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: z = APPNP(z0) = 10 fused hops
+z <- 0.9 * A_hat z + 0.1 * z0 over nnz = E + N edges, z0 [N, 47] fp32 (appnp_stack.py:22,30).
+value = aggregated edges / s (GTEPS) over all ranks, inputs resident in HBM.
+e2e   = the same metric through the host-buffer C-ABI call (rgbmp_appnp_host): H2D of z0 from
+        pinned memory, 10 hops, D2H of z inside the timed region.
+--impl reference times the reference's CPU path (the oracle's restated PyG gather -> scale ->
+scatter_add_, this tier's definition) on the host cores, rank 0 only.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "products"
+K_HOPS, ALPHA, F_CLASSES = 10, 0.1, 47
+GRAPH_SEED = 20261018
+CPU_SAMPLE_FRACTION = 0.10          # share of the target rows used by the bounded CPU sample
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def algorithmic_bytes_per_hop(nnz: int, n: int, F: int, weighted: bool) -> int:
+    """SURVEY.md 8d gather model, no cache credit: nnz*(F*4 + 4 [col] + s_w) + N*F*4 [store]
+    + (N+1)*8 [rowptr] + N*F*4 [teleport read]."""
+    return nnz * (F * 4 + 4 + (4 if weighted else 0)) + n * F * 4 + (n + 1) * 8 + n * F * 4
+
+
+def make_workload(device):
+    import rgb_experiment_b200.synth as S
+    return S.make_named(WORKLOAD, seed=GRAPH_SEED, device=device, features=False)
+
+
+def cpu_sample(sg, device):
+    """Bounded CPU sample of the same workload: the edges (after add_remaining_self_loops) whose
+    target is one of the first 10% of the nodes, with their gcn_norm weights, and z [N, 47]."""
+    N = sg.num_nodes
+    ei = sg.edge_index
+    loop = torch.arange(N, device=ei.device)
+    src = torch.cat([ei[0], loop])
+    dst = torch.cat([ei[1], loop])
+    deg = torch.bincount(dst, minlength=N).float()
+    dinv = deg.pow(-0.5)
+    n_sub = int(N * CPU_SAMPLE_FRACTION)
+    m = dst < n_sub
+    s, d = src[m], dst[m]
+    w = dinv[s] * dinv[d]
+    z = torch.randn(N, F_CLASSES, generator=torch.Generator().manual_seed(1))
+    return s.cpu(), d.cpu(), w.cpu(), z, n_sub
+
+
+def cpu_hop(s, d, w, z, n_sub, alpha=ALPHA):
+    """The literal PyG-on-CPU form (oracle.pyg_restated.propagate): index_select -> mul -> scatter_add_."""
+    from oracle import pyg_restated as R
+    out = R.scatter_add(w.view(-1, 1) * z.index_select(0, s), d, dim=0, dim_size=n_sub)
+    out = out * (1 - alpha)
+    return out + alpha * z[:n_sub]
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    sg = make_workload(dev)
+    s, d, w, z, n_sub = cpu_sample(sg, dev)
+    del sg
+    cores = torch.get_num_threads()
+    for _ in range(args.warmup):
+        cpu_hop(s, d, w, z, n_sub)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_hop(s, d, w, z, n_sub)
+    dt = time.perf_counter() - t0
+    val = s.numel() * args.steps / dt / 1e9
+    sample = (f"1 hop per step over the {s.numel()} edges whose target is in the first "
+              f"{int(CPU_SAMPLE_FRACTION * 100)}% of nodes; literal index_select->mul->scatter_add_ fp32")
+    line = {"impl": "reference", "metric": "appnp_propagate_gteps", "value": val, "unit": "GTEPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}-shaped R-MAT graph, APPNP hop F={F_CLASSES} (CPU sample)"},
+            "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fold", type=int, default=0, help="1: fold D^-1/2 into row scaling (no per-edge weights)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import rgb_experiment_b200 as P
+    import rgb_experiment_b200.partition as PT
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sg = make_workload(dev)
+    N, F = sg.num_nodes, F_CLASSES
+    t0 = time.perf_counter()
+    if world == 1:
+        g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        nnz = g.nnz
+        n_items = g.fwd.n_items
+        z0 = torch.randn(N, F, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        z0p, ld = P.ops.as_rows(z0)
+        val = None if args.fold else g.gcn_val(False)
+
+        def step():
+            return P.ops._appnp_khop(g.fwd, g, z0p, K_HOPS, ALPHA, False, bool(args.fold))
+
+        launches_per_step = K_HOPS * (1 + (2 if n_items > 0 else 0)) + (1 if args.fold else 0)
+    else:
+        blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, rank, world)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        nnz = blk.nnz_global
+        prop = PT.PartitionedAPPNP(blk, F)
+        z0l = torch.zeros((blk.R, prop.ld), device=dev)
+        z0l[: blk.hi - blk.lo, :F] = torch.randn(blk.hi - blk.lo, F, device=dev,
+                                                 generator=torch.Generator(device=dev).manual_seed(1 + rank))
+
+        def step():
+            return prop.run(z0l, K_HOPS, ALPHA)
+
+        launches_per_step = K_HOPS * prop.launches_per_hop
+    del sg
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    gteps = nnz * K_HOPS * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI host entry point (single GPU) / host round trip (multi) ----
+    e2e = None
+    if world == 1:
+        z0h = z0.cpu().pin_memory()
+        outh = torch.empty_like(z0h).pin_memory()
+        plan = P.ops.HostAppnpPlan(g, F)
+        for _ in range(2):
+            P.ops.appnp_host(g, z0h, outh, K_HOPS, ALPHA, plan)
+        torch.cuda.synchronize()
+        n_e2e = max(3, args.steps // 2)
+        w0 = time.perf_counter()
+        for _ in range(n_e2e):
+            P.ops.appnp_host(g, z0h, outh, K_HOPS, ALPHA, plan)      # returns after the D2H completed
+        wall = time.perf_counter() - w0
+        e2e = {"value": nnz * K_HOPS * n_e2e / wall / 1e9, "unit": "GTEPS",
+               "h2d_bytes_per_step": N * F * 4, "d2h_bytes_per_step": N * F * 4, "ms_per_step": wall / n_e2e * 1e3}
+    else:
+        R_, ldp = z0l.shape
+        z0h = z0l.cpu().pin_memory()
+        outh = torch.empty_like(z0h).pin_memory()
+        n_e2e = max(3, args.steps // 2)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(n_e2e):
+            z0l.copy_(z0h, non_blocking=True)
+            outh.copy_(step(), non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - w0], device=dev)
+        dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        wall = float(wall.item())
+        e2e = {"value": nnz * K_HOPS * n_e2e / wall / 1e9, "unit": "GTEPS",
+               "h2d_bytes_per_step": R_ * ldp * 4 * world, "d2h_bytes_per_step": R_ * ldp * 4 * world,
+               "ms_per_step": wall / n_e2e * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = peaks()
+    hop_bytes = algorithmic_bytes_per_hop(nnz // world, N // world, F, weighted=not args.fold)
+    hop_ms = ms_per_step / K_HOPS
+    achieved = hop_bytes / (hop_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "kernel": "spmm_rows_kernel<float,4,...> (+long/combine)",
+                "bytes_per_launch": hop_bytes, "launch_ms": hop_ms}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("spmm_rows_kernel_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sg2 = make_workload(dev)
+        s, d, w, z, n_sub = cpu_sample(sg2, dev)
+        del sg2
+        cpu_hop(s, d, w, z, n_sub)
+        best = None
+        tot0 = time.perf_counter()
+        hops = 0
+        while hops < 10 and time.perf_counter() - tot0 < 25:
+            c0 = time.perf_counter()
+            cpu_hop(s, d, w, z, n_sub)
+            dt = time.perf_counter() - c0
+            best = dt if best is None else min(best, dt)
+            hops += 1
+        cpu_baseline = {"value": s.numel() / best / 1e9, "unit": "GTEPS", "cores": torch.get_num_threads(),
+                        "kind": "port",
+                        "sample": f"best of {hops} single hops over the {s.numel()} edges whose target is in the first "
+                                  f"{int(CPU_SAMPLE_FRACTION * 100)}% of nodes; literal index_select->mul->scatter_add_ fp32"}
+
+    line = {"metric": "appnp_propagate_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"APPNP K={K_HOPS} alpha={ALPHA} propagate, ogbn-products-shaped R-MAT graph "
+                                   f"(N={N}, E={nnz - N} directed + {N} self loops, F={F} fp32)",
+                       "hops_per_step": K_HOPS, "nnz": nnz, "parallelism": f"row-partition x{world}" if world > 1 else "single",
+                       "l2": "inputs larger than L2 (features 470 MB, col 505 MB vs 126 MB L2)",
+                       "norm": "folded" if args.fold else "per-edge weights", "graph_build_ms": build_ms},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": sampler.result()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

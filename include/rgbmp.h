@@ -1,0 +1,261 @@
+/*
+ * rgbmp.h -- C ABI of the B200-native message-passing library (librgbmp.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of PolarisRisingWar/rgb-experiment:
+ * the neighbourhood aggregation that its model files delegate to torch_geometric /
+ * torch_scatter / torch_sparse.  The reference has no FFI of its own
+ * (pure Python); each entry point below cites the reference call site whose third-party
+ * operator it replaces.  The Python host side (rgb-experiment_b200/) binds these with ctypes
+ * and exposes them under the PyG names the reference imports.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *     the library never allocates, frees or retains pointers past the call;
+ *   - scratch memory comes from a caller-provided workspace sized by the *_workspace_bytes query;
+ *   - `device` is the CUDA ordinal, `stream` a cudaStream_t passed as void*; nothing here
+ *     synchronises the device (only the *_host entry points wait, on their own stream);
+ *   - return value: 0 ok; >0 a cudaError_t; <0 an argument error (RGBMP_E*);
+ *     rgbmp_last_error() returns a per-thread message; nothing is printed, nothing throws;
+ *   - all functions are re-entrant (autograd calls backward from its own worker thread);
+ *   - features are row-major [rows, F] with an explicit leading dimension in ELEMENTS;
+ *     dtype is RGBMP_F32 or RGBMP_BF16 (bf16 storage, fp32 accumulation);
+ *   - node ids / column indices are int32 (N < 2^31), row pointers int64, edge ids int32
+ *     (nnz < 2^31 per GPU partition).
+ */
+#ifndef RGBMP_H_
+#define RGBMP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define RGBMP_VERSION 100
+
+/* argument errors */
+#define RGBMP_EINVAL   (-1)  /* null pointer / bad enum / negative size */
+#define RGBMP_EALIGN   (-2)  /* pointer or leading dimension not aligned for the vector path */
+#define RGBMP_ERANGE   (-3)  /* N, F or nnz out of the supported range (32-bit overflow) */
+#define RGBMP_EWORKSPACE (-4) /* workspace too small */
+
+/* dtypes */
+#define RGBMP_F32  0
+#define RGBMP_BF16 1
+
+/* self-loop edit applied before aggregation */
+#define RGBMP_LOOP_NONE            0  /* LabelPropagation / C&S: gcn_norm(add_self_loops=False)           */
+#define RGBMP_LOOP_ADD             1  /* add_self_loops                    (graphsage.py:56)              */
+#define RGBMP_LOOP_ADD_REMAINING   2  /* add_remaining_self_loops          (dagnn.py:22-23; GCNConv/APPNP/SGConv/FAConv) */
+#define RGBMP_LOOP_REMOVE_THEN_ADD 3  /* remove_self_loops+add_self_loops  (graphsage.py:55-56; GATConv/SuperGATConv)    */
+
+/* node-normalisation vectors derived from the row pointer */
+#define RGBMP_NORM_INV_SQRT 0  /* deg^-1/2, inf -> 0   (dagnn.py:27-30 gcn_norm)                        */
+#define RGBMP_NORM_INV_MEAN 1  /* 1/max(deg,1)                                                          */
+#define RGBMP_NORM_COUNT    2  /* max(deg,1)           (aggr='mean', graphsage.py:39 -> scatter mean divides by it) */
+
+int         rgbmp_version(void);
+const char* rgbmp_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) integer graph-build kernels -- bit-exact against oracle.pyg_restated.{edit_loops,csr_build}
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces remove_self_loops / add_self_loops / add_remaining_self_loops
+ * (reference call sites graphsage.py:55-56, dagnn.py:22-23; inside GCNConv gcn.py:18-21 etc.).
+ * In : src,dst int64 [E] (= edge_index[0], edge_index[1]).
+ * Out: e_src,e_dst int32 [E+N] -- kept edges in original order then loops 0..N-1;
+ *      nnz_dev int64 [1] (device) -- number of valid entries written. */
+size_t rgbmp_edge_edit_workspace_bytes(int64_t E, int64_t N);
+int rgbmp_edge_edit(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int loop_mode,
+                    int32_t* e_src, int32_t* e_dst, int64_t* nnz_dev,
+                    void* ws, size_t ws_bytes, int device, void* stream);
+
+/* Stable counting/radix sort of an edge list by `key` -> CSR.  No reference counterpart (PyG
+ * stays COO and scatters with atomics); definition = oracle csr_build:
+ * perm = argsort(key, stable); rowptr = [0, cumsum(bincount(key))]; col = other[perm]; eid = perm.
+ * Forward CSR: key = e_dst, other = e_src.  Transpose CSR (backward): key = e_src, other = e_dst. */
+size_t rgbmp_csr_build_workspace_bytes(int64_t nnz, int64_t N);
+int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64_t N,
+                    int64_t* rowptr, int32_t* col, int32_t* eid,
+                    void* ws, size_t ws_bytes, int device, void* stream);
+
+/* deg = rowptr[i+1]-rowptr[i] -> node vector (dagnn.py:27-30 / scatter-mean count clamp). */
+int rgbmp_degree_norm(const int64_t* rowptr, int64_t N, int mode, float* out, int device, void* stream);
+
+/* Per-edge symmetric weights in CSR order: val[k] = dinv_col[col[k]] * 1.0f * dinv_row[i]
+ * (dagnn.py:31: deg_inv_sqrt[row] * edge_weight * deg_inv_sqrt[col], same multiplication order). */
+int rgbmp_gcn_edge_weight(const int64_t* rowptr, const int32_t* col, int64_t n_rows,
+                          const float* dinv_row, const float* dinv_col, float* val,
+                          int device, void* stream);
+
+/* Permute a per-edge array between edge order and CSR order: out[k] = in[eid[k]]  (gather)
+ * or out[eid[k]] = in[k] (scatter).  H contiguous floats per edge. */
+int rgbmp_edge_permute(const float* in, const int32_t* eid, int64_t nnz, int H, int scatter,
+                       float* out, int device, void* stream);
+
+/* Long-row split: rows with more than `chunk` edges are processed as work items of
+ * `long_chunk` edges each.  Step 1 counts (results in counts_dev[0]=n_long, [1]=n_items),
+ * step 2 fills the lists once the caller has allocated them. */
+int rgbmp_longrow_count(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk,
+                        int64_t* counts_dev, int device, void* stream);
+size_t rgbmp_longrow_fill_workspace_bytes(int64_t n_rows);
+int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk,
+                       int64_t n_long, int64_t n_items,
+                       int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long, int64_t* item_start,
+                       void* ws, size_t ws_bytes, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) aggregation kernels
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct rgbmp_graph {
+  int64_t        n_rows;       /* rows of this CSR (targets i for forward, sources j for transpose) */
+  int64_t        n_cols;       /* number of addressable feature rows (max col + 1)                  */
+  int64_t        nnz;
+  const int64_t* rowptr;       /* [n_rows+1]                                                        */
+  const int32_t* col;          /* [nnz]                                                             */
+  int32_t        chunk;        /* rows with deg > chunk are "long" (0 = no split information)       */
+  int32_t        long_chunk;
+  int64_t        n_long;
+  int64_t        n_items;
+  const int32_t* long_rows;    /* [n_long]                                                          */
+  const int32_t* long_item_ptr;/* [n_long+1]                                                        */
+  const int32_t* item_long;    /* [n_items]                                                         */
+  const int64_t* item_start;   /* [n_items]                                                         */
+} rgbmp_graph_t;
+
+/* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
+ *   v = row_scale ? (row_div ? s_i / row_scale[i] : row_scale[i]*s_i) : s_i
+ *   if reset_when==1 and reset_mask[i]: v = reset_val[i,:]          (PTA label_propagation,
+ *                                                                    itexperiments.py:715-717)
+ *   v = a*v + (T ? b*T[i,:] : 0)                                     (APPNP appnp_stack.py:22,
+ *                                                                    PTA pta.py:83, LP A15)
+ *   if clamp: v = min(max(v,lo),hi)                                  (C&S post_step, A15)
+ *   if reset_when==2 and reset_mask[i]: v = reset_val[i,:]           (C&S autoscale=False)
+ *   Y[i,:] = v (if Y) ;  Y2[i,:] = out2_scale[i]*v (if Y2)           (pre-scaled copy for the next hop)
+ */
+typedef struct rgbmp_epilogue {
+  const float*   row_scale;
+  int32_t        row_div;      /* 1: divide by row_scale[i] (scatter-mean's true divide) */
+  const uint8_t* reset_mask;
+  const float*   reset_val;
+  int64_t        ld_reset;
+  int32_t        reset_when;
+  float          a;
+  float          b;
+  const void*    T;            /* same dtype as X */
+  int64_t        ldt;
+  int32_t        clamp;
+  float          lo, hi;
+  const float*   out2_scale;
+  void*          Y2;
+  int64_t        ldy2;
+} rgbmp_epilogue_t;
+
+/* CSR SpMM  Y[i,:] = epilogue( sum_k val[k] * X[col[k],:] ), k in rowptr[i]..rowptr[i+1].
+ * Replaces MessagePassing.propagate = index_select -> message -> scatter
+ * (graphsage.py:58, dagnn.py:46,57-59; inside GCNConv gcn.py:27,29, SAGEConv, GINConv, ...).
+ * val may be NULL (unweighted sum / mean via row_scale).  The same call on the transpose CSR is
+ * the backward.  `tune` = 0 picks the launch shape heuristically; otherwise (G | V<<8 | U<<16). */
+size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F);
+int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx,
+               void* Y, int64_t ldy, int F, int dtype, const rgbmp_epilogue_t* ep, int tune,
+               void* ws, size_t ws_bytes, int device, void* stream);
+
+/* Fused K-hop propagation (APPNP appnp_stack.py:22; SGConv sgc.py:9-10; Prop dagnn.py:45-47;
+ * PTA.inference pta.py:82-83; label_propagation itexperiments.py:714-718; LabelPropagation /
+ * CorrectAndSmooth itexperiments.py:525-526).  Hop k reads the previous iterate and writes the
+ * next through ping/pong; the epilogue (teleport, clamp, reset, re-scaling for the folded
+ * D^-1/2 normalisation) is applied inside the SpMM kernel of every hop.
+ *   X0         first-hop input (already multiplied by out2_scale when the normalisation is folded)
+ *   ping,pong  [n_rows, ldp] intermediates (only touched when K > 1)
+ *   out        final iterate (unscaled)
+ *   hops       optional [K][n_rows, ld_hops] -- every hop's unscaled output (DAGNN keeps them) */
+int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t ldx0,
+               void* ping, void* pong, int64_t ldp, void* out, int64_t ldo,
+               void* hops, int64_t ld_hops, int64_t hop_stride,
+               int F, int dtype, int K, const rgbmp_epilogue_t* ep, int tune,
+               void* ws, size_t ws_bytes, int device, void* stream);
+
+/* Y[i,:] = scale[i] * X[i,:]  (the D^-1/2 pre-scaling of the folded normalisation), or with
+ * divide=1  Y[i,:] = X[i,:] / scale[i]  (backward of scatter-mean: grad / count). */
+int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, void* Y, int64_t ldy,
+                    int64_t n_rows, int F, int dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (c) attention kernels
+ * ------------------------------------------------------------------------------------------ */
+
+/* Fused GATConv edge-softmax + weighted aggregate (gat.py:18-21,28-30).
+ *   Xp [N,H*C] (ldx), a_src [n_cols,H], a_dst [n_rows,H]; per row i over in-edges j:
+ *   e = leaky_relu(a_src[j]+a_dst[i]); alpha = exp(e-max)/(sum+1e-16); out[i] = sum alpha*Xp[j].
+ * Saves rowmax,rowsum [n_rows,H] for the backward.  drop (optional, CSR order [nnz,H]) is the
+ * attention-dropout keep-mask already divided by (1-p). */
+size_t rgbmp_gat_workspace_bytes(const rgbmp_graph_t* g, int H, int C);
+int rgbmp_gat_forward(const rgbmp_graph_t* g, const float* Xp, int64_t ldx,
+                      const float* a_src, const float* a_dst, int H, int C, float slope,
+                      const float* drop, float* out, int64_t ldo, float* rowmax, float* rowsum,
+                      void* ws, size_t ws_bytes, int device, void* stream);
+
+/* Backward on the TRANSPOSE CSR gT (rows = sources j).  S[i,h] = <dout[i,h,:], out[i,h,:]> is
+ * computed by rgbmp_rowdot.  Writes dXp [n_src,H*C], da_src [n_src,H]; accumulates da_dst
+ * [n_dst,H] (must be zero on entry).  eid_map_T: for drop (CSR order) lookup, tpos[k'] gives the
+ * forward-CSR position of transpose entry k' (NULL when drop is NULL). */
+int rgbmp_gat_backward(const rgbmp_graph_t* gT, const float* Xp, int64_t ldx,
+                       const float* a_src, const float* a_dst, int H, int C, float slope,
+                       const float* drop, const int32_t* tpos,
+                       const float* rowmax, const float* rowsum, const float* S,
+                       const float* dout, int64_t ldd,
+                       float* dXp, int64_t lddx, float* da_src, float* da_dst,
+                       int device, void* stream);
+
+/* S[i,h] = sum_c A[i,h*C+c]*B[i,h*C+c] */
+int rgbmp_rowdot(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n_rows,
+                 int H, int C, float* S, int device, void* stream);
+
+/* Generic edge-score kernels in CSR order (SuperGATConv supergat.py:15-21, FAConv fagcn.py:15):
+ *  SDDMM      out[k,h] = <A[row_i,h,:], B[col[k],h,:]>
+ *  u_add_v    out[k,h] = u[col[k],h] + v[row_i,h]
+ *  seg_softmax per-row softmax over k (max-subtracted, /(sum+1e-16)), in place capable.
+ *  seg_sum     out[i,h] = sum_k in[k,h]        (deterministic segmented reduce)               */
+int rgbmp_sddmm(const rgbmp_graph_t* g, const float* A, int64_t lda, const float* B, int64_t ldb,
+                int H, int C, float* out, int device, void* stream);
+int rgbmp_u_add_v(const rgbmp_graph_t* g, const float* u, const float* v, int H, float* out,
+                  int device, void* stream);
+int rgbmp_seg_softmax(const rgbmp_graph_t* g, const float* in, int H, float* out,
+                      int device, void* stream);
+int rgbmp_seg_softmax_backward(const rgbmp_graph_t* g, const float* alpha, const float* dalpha,
+                               int H, float* dlogit, int device, void* stream);
+int rgbmp_seg_sum(const rgbmp_graph_t* g, const float* in, int H, float* out,
+                  int device, void* stream);
+/* weighted multi-head SpMM: out[i,h,:] = sum_k w[k,h] * X[col[k],h,:]  (w in CSR order) */
+int rgbmp_spmm_heads(const rgbmp_graph_t* g, const float* w, const float* X, int64_t ldx,
+                     int H, int C, float* out, int64_t ldo, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (d) host-buffer entry point (end-to-end form of the hot path: H2D -> K hops -> D2H)
+ * ------------------------------------------------------------------------------------------ */
+
+/* APPNP-style K-hop propagation with HOST input/output (pinned or pageable):
+ *   z = z0; K x { z = (1-alpha) * D^-1/2 (A+I) D^-1/2 z + alpha * z0 }
+ * The graph (g, dinv) is device-resident, like the reference keeps edge_index on the device
+ * across epochs (itexperiments.py:258).  dev_* are caller-provided device scratch buffers
+ * [n_rows, ld] each.  Copies and kernels are enqueued on `stream`, which is synchronised
+ * before returning. */
+int rgbmp_appnp_host(const rgbmp_graph_t* g, const float* dinv,
+                     const float* z0_host, float* out_host, int F, int K, float alpha,
+                     float* dev_z0, float* dev_ping, float* dev_pong, float* dev_out, int64_t ld,
+                     void* ws, size_t ws_bytes, int device, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBMP_H_ */

@@ -40,12 +40,20 @@ def install_matplotlib_stub():
             return _Anything()
 
         def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
             return _Anything()
 
     mpl = _mod("matplotlib", use=lambda *a, **k: None, rcParams={})
     fm = _mod("matplotlib.font_manager", FontProperties=_Anything)
     plt = types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Anything()      # type: ignore[attr-defined]
+
+    def _plt_getattr(name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
+    plt.__getattr__ = _plt_getattr                   # type: ignore[attr-defined]
     mpl.font_manager, mpl.pyplot = fm, plt
     sys.modules.update({"matplotlib": mpl, "matplotlib.font_manager": fm, "matplotlib.pyplot": plt})
     return True

@@ -1,0 +1,589 @@
+// Integer graph-build kernels (sm_100a): self-loop edit, stable radix sort -> CSR / transpose CSR,
+// degree normalisation, long-row work lists.  Bit-exact against oracle.pyg_restated
+// {edit_loops, csr_build, degree}.  All HBM-bound integer work: coalesced streaming reads,
+// shared-memory digit counters, grids sized from the data (one tile per CTA).
+#include "common.cuh"
+
+namespace rgbmp {
+
+// ---------------------------------------------------------------------------------------------
+// generic exclusive scan (3-phase, in place)
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total via smem
+template <typename T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total, T* smem /*THREADS/32+1*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T inc = warp_inclusive_scan(v, lane);
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    T w = (lane < THREADS / 32) ? smem[lane] : T(0);
+    T winc = warp_inclusive_scan(w, lane);
+    if (lane < THREADS / 32) smem[lane] = winc - w;
+    if (lane == THREADS / 32 - 1) smem[THREADS / 32] = winc;
+  }
+  __syncthreads();
+  T res = inc - v + smem[warp];
+  *total = smem[THREADS / 32];
+  __syncthreads();
+  return res;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(T* data, int64_t n, T* sums) {
+  __shared__ T sm[SCAN_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  T v[SCAN_ITEMS];
+  T local = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < n) ? data[base + i] : T(0);
+    local += v[i];
+  }
+  T total;
+  T pre = block_exclusive_scan<T, SCAN_THREADS>(local, &total, sm);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) data[base + i] = pre;
+    pre += v[i];
+  }
+  if (threadIdx.x == 0 && sums) sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(T* data, int64_t n, const T* sums) {
+  const T add = sums[blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < n) data[base + i] += add;
+}
+
+inline size_t scan_ws_elems(int64_t n) {
+  size_t tot = 0;
+  while (n > 1) {
+    n = ceil_div(n, SCAN_TILE);
+    tot += align_up((size_t)n, 64);
+    if (n == 1) break;
+  }
+  return tot + 64;
+}
+
+// in-place exclusive scan of data[0..n); `ws` holds scan_ws_elems(n) elements of T
+template <typename T>
+cudaError_t exclusive_scan(T* data, int64_t n, T* ws, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t nb = ceil_div(n, SCAN_TILE);
+  if (nb == 1) {
+    scan_tile_kernel<T><<<1, SCAN_THREADS, 0, st>>>(data, n, nullptr);
+    return cudaGetLastError();
+  }
+  scan_tile_kernel<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(data, n, ws);
+  cudaError_t e = exclusive_scan<T>(ws, nb, ws + align_up((size_t)nb, 64), st);
+  if (e != cudaSuccess) return e;
+  scan_add_kernel<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(data, n, ws);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge edit: stable compaction of non-loop edges + loop append   
+// ---------------------------------------------------------------------------------------------
+constexpr int EE_THREADS = 256;
+constexpr int EE_ITEMS = 8;
+constexpr int EE_TILE = EE_THREADS * EE_ITEMS;
+
+__global__ void __launch_bounds__(EE_THREADS)
+ee_count_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int64_t N,
+                int filter, int32_t* __restrict__ blockcnt, int32_t* __restrict__ errflag) {
+  __shared__ int32_t sm[EE_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * EE_TILE;
+  int32_t c = 0;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < EE_ITEMS; ++i) {
+    const int64_t e = base + (int64_t)i * EE_THREADS + threadIdx.x;
+    if (e < E) {
+      const int64_t s = src[e], d = dst[e];
+      bad |= ((uint64_t)s >= (uint64_t)N) | ((uint64_t)d >= (uint64_t)N);
+      c += (!filter || s != d) ? 1 : 0;
+    }
+  }
+  int32_t total;
+  block_exclusive_scan<int32_t, EE_THREADS>(c, &total, sm);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = total;
+  if (bad) atomicOr(errflag, 1);
+}
+
+// thread t owns EE_ITEMS CONSECUTIVE edges so that the compaction is stable with one scan
+__global__ void __launch_bounds__(EE_THREADS)
+ee_write_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int filter,
+                const int32_t* __restrict__ blockoff, int32_t* __restrict__ e_src, int32_t* __restrict__ e_dst) {
+  __shared__ int32_t sm[EE_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * EE_TILE + (int64_t)threadIdx.x * EE_ITEMS;
+  int32_t s[EE_ITEMS], d[EE_ITEMS];
+  bool keep[EE_ITEMS];
+  int32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < EE_ITEMS; ++i) {
+    const int64_t e = base + i;
+    keep[i] = false;
+    if (e < E) {
+      s[i] = (int32_t)src[e];
+      d[i] = (int32_t)dst[e];
+      keep[i] = (!filter || s[i] != d[i]);
+    }
+    c += keep[i] ? 1 : 0;
+  }
+  int32_t total;
+  int32_t pos = blockoff[blockIdx.x] + block_exclusive_scan<int32_t, EE_THREADS>(c, &total, sm);
+#pragma unroll
+  for (int i = 0; i < EE_ITEMS; ++i) {
+    if (keep[i]) {
+      e_src[pos] = s[i];
+      e_dst[pos] = d[i];
+      ++pos;
+    }
+  }
+}
+
+// the count kernel must see the same thread->edge mapping only in aggregate (per block), so the
+// strided mapping there is fine; both kernels cover edges [block*TILE, (block+1)*TILE).
+
+__global__ void ee_loops_kernel(int64_t N, int add_loops, const int32_t* __restrict__ blockoff, int64_t nblocks,
+                                const int32_t* __restrict__ lastcnt_src, int64_t E_fixed,
+                                int32_t* __restrict__ e_src, int32_t* __restrict__ e_dst,
+                                int64_t* __restrict__ nnz_dev, const int32_t* __restrict__ errflag) {
+  // kept = (filter path) blockoff[nblocks-1] + lastcnt  |  (no filter) E_fixed
+  int64_t kept = E_fixed;
+  if (blockoff) kept = (nblocks > 0) ? (int64_t)blockoff[nblocks - 1] + (int64_t)lastcnt_src[0] : 0;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (add_loops && i < N) {
+    e_src[kept + i] = (int32_t)i;
+    e_dst[kept + i] = (int32_t)i;
+  }
+  if (i == 0) nnz_dev[0] = (*errflag) ? -1 : kept + (add_loops ? N : 0);
+}
+
+__global__ void ee_save_last_kernel(const int32_t* blockcnt, int64_t nblocks, int32_t* last) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) last[0] = nblocks > 0 ? blockcnt[nblocks - 1] : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort (8-bit digits) of (key, value=edge id)
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per CTA
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, int64_t nblocks,
+               int32_t* __restrict__ blockhist /*[256][nblocks]*/) {
+  __shared__ int32_t h[RS_BINS];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int64_t k = base + (int64_t)i * RS_THREADS + threadIdx.x;
+    if (k < n) atomicAdd(&h[((uint32_t)keys[k] >> shift) & 0xFF], 1);
+  }
+  __syncthreads();
+  blockhist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// Warp w ranks the contiguous slice [w*512, (w+1)*512) of the tile in 16 rounds of 32 keys, so the
+// (round, lane) order is the input order: ranks are stable.
+template <bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
+                  int64_t nblocks, const int32_t* __restrict__ blockoff /*scanned [256][nblocks]*/,
+                  int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+  __shared__ int32_t cnt[RS_WARPS][RS_BINS];
+  __shared__ int32_t gbase[RS_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+  int32_t key[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    const bool valid = k < n;
+    key[r] = valid ? keys_in[k] : 0;
+    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    int32_t old = 0;
+    if (valid && lane == leader) {
+      old = cnt[warp][d];
+      cnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread d: exclusive scan over warps for digit d; fetch the tile's global base
+    const int d = threadIdx.x;
+    int32_t off = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const int32_t c = cnt[w][d];
+      cnt[w][d] = off;
+      off += c;
+    }
+    gbase[d] = blockoff[(int64_t)d * nblocks + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    if (k < n) {
+      const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+      const int32_t pos = gbase[d] + cnt[warp][d] + rank[r];
+      keys_out[pos] = key[r];
+      vals_out[pos] = FIRST ? (int32_t)k : vals_in[k];
+    }
+  }
+}
+
+__global__ void deg_hist_kernel(const int32_t* __restrict__ key, int64_t nnz, unsigned long long* __restrict__ deg) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
+    atomicAdd(&deg[key[k]], 1ull);
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n,
+                                  int32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = src[idx[k]];
+}
+
+__global__ void iota_i32_kernel(int32_t* out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = (int32_t)k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// node / edge normalisation
+// ---------------------------------------------------------------------------------------------
+__global__ void degree_norm_kernel(const int64_t* __restrict__ rowptr, int64_t N, int mode, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float deg = (float)(rowptr[i + 1] - rowptr[i]);
+  float v;
+  if (mode == RGBMP_NORM_INV_SQRT) {
+    v = (deg > 0.f) ? __fdiv_rn(1.0f, __fsqrt_rn(deg)) : 0.f;  // IEEE 1/sqrt == torch CPU pow(-0.5); inf -> 0
+  } else if (mode == RGBMP_NORM_INV_MEAN) {
+    v = __fdiv_rn(1.0f, fmaxf(deg, 1.0f));
+  } else {
+    v = fmaxf(deg, 1.0f);
+  }
+  out[i] = v;
+}
+
+__global__ void gcn_edge_weight_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                       int64_t n_rows, const float* __restrict__ dinv_row,
+                                       const float* __restrict__ dinv_col, float* __restrict__ val) {
+  // one warp per row
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float di = dinv_row[row];
+  const int64_t s = rowptr[row], e = rowptr[row + 1];
+  for (int64_t k = s + lane; k < e; k += 32)
+    val[k] = __fmul_rn(__fmul_rn(dinv_col[col[k]], 1.0f), di);  // dinv[src]*w*dinv[dst], w = 1
+}
+
+__global__ void edge_permute_kernel(const float* __restrict__ in, const int32_t* __restrict__ eid, int64_t nnz, int H,
+                                    int scatter, float* __restrict__ out) {
+  const int64_t total = nnz * H;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t k = t / H;
+    const int h = (int)(t - k * H);
+    const int64_t e = eid[k];
+    if (scatter) out[e * H + h] = in[t];
+    else out[t] = in[e * H + h];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// long-row work lists
+// ---------------------------------------------------------------------------------------------
+__global__ void longrow_count_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk,
+                                     int32_t long_chunk, unsigned long long* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nl = 0, ni = 0;
+  if (i < n_rows) {
+    const int64_t deg = rowptr[i + 1] - rowptr[i];
+    if (deg > chunk) {
+      nl = 1;
+      ni = (unsigned long long)((deg + long_chunk - 1) / long_chunk);
+    }
+  }
+  // warp-aggregate before the global atomics
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nl += __shfl_down_sync(0xffffffffu, nl, o);
+    ni += __shfl_down_sync(0xffffffffu, ni, o);
+  }
+  if ((threadIdx.x & 31) == 0 && nl) {
+    atomicAdd(&counts[0], nl);
+    atomicAdd(&counts[1], ni);
+  }
+}
+
+__global__ void longrow_flags_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk,
+                                     int32_t long_chunk, int32_t* __restrict__ slot, int32_t* __restrict__ items) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t deg = rowptr[i + 1] - rowptr[i];
+  const bool lg = deg > chunk;
+  slot[i] = lg ? 1 : 0;
+  items[i] = lg ? (int32_t)((deg + long_chunk - 1) / long_chunk) : 0;
+}
+
+__global__ void longrow_fill_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk,
+                                    int32_t long_chunk, const int32_t* __restrict__ slot,
+                                    const int32_t* __restrict__ items, int64_t n_long, int64_t n_items,
+                                    int32_t* __restrict__ long_rows, int32_t* __restrict__ long_item_ptr,
+                                    int32_t* __restrict__ item_long, int64_t* __restrict__ item_start) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) long_item_ptr[n_long] = (int32_t)n_items;
+  if (i >= n_rows) return;
+  const int64_t s = rowptr[i], deg = rowptr[i + 1] - s;
+  if (deg <= chunk) return;
+  const int32_t sl = slot[i], it0 = items[i];
+  long_rows[sl] = (int32_t)i;
+  long_item_ptr[sl] = it0;
+  const int32_t cnt = (int32_t)((deg + long_chunk - 1) / long_chunk);
+  for (int32_t j = 0; j < cnt; ++j) {
+    item_long[it0 + j] = sl;
+    item_start[it0 + j] = s + (int64_t)j * long_chunk;
+  }
+}
+
+}  // namespace rgbmp
+
+using namespace rgbmp;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int rgbmp_version(void) { return RGBMP_VERSION; }
+const char* rgbmp_last_error(void) { return err_buf(); }
+
+size_t rgbmp_edge_edit_workspace_bytes(int64_t E, int64_t N) {
+  (void)N;
+  const size_t nb = (size_t)ceil_div(E > 0 ? E : 1, EE_TILE);
+  return (align_up(nb, 64) + scan_ws_elems((int64_t)nb) + 128) * sizeof(int32_t) + 1024;
+}
+
+int rgbmp_edge_edit(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int loop_mode, int32_t* e_src,
+                    int32_t* e_dst, int64_t* nnz_dev, void* ws, size_t ws_bytes, int device, void* stream) {
+  if (E < 0 || N < 0 || (E > 0 && (!src || !dst)) || !e_src || !e_dst || !nnz_dev || !ws)
+    return fail(RGBMP_EINVAL, "rgbmp_edge_edit: null pointer or negative size");
+  if (loop_mode < 0 || loop_mode > 3) return fail(RGBMP_EINVAL, "rgbmp_edge_edit: bad loop_mode %d", loop_mode);
+  if (N >= (1ll << 31) - 1 || E + N >= (1ll << 31) - 1)
+    return fail(RGBMP_ERANGE, "rgbmp_edge_edit: N=%lld, E+N=%lld exceed the int32 id range", (long long)N,
+                (long long)(E + N));
+  if (ws_bytes < rgbmp_edge_edit_workspace_bytes(E, N)) return fail(RGBMP_EWORKSPACE, "rgbmp_edge_edit: workspace");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_edge_edit: bad device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int filter = (loop_mode == RGBMP_LOOP_ADD_REMAINING || loop_mode == RGBMP_LOOP_REMOVE_THEN_ADD) ? 1 : 0;
+  const int add_loops = loop_mode != RGBMP_LOOP_NONE;
+  const int64_t nb = ceil_div(E, EE_TILE);
+  Carver cv(ws, ws_bytes);
+  int32_t* errflag = cv.take<int32_t>(1);
+  int32_t* last = cv.take<int32_t>(1);
+  int32_t* blockcnt = cv.take<int32_t>(align_up((size_t)(nb > 0 ? nb : 1), 64));
+  int32_t* scanws = cv.take<int32_t>(scan_ws_elems(nb > 0 ? nb : 1));
+  RGBMP_CUDA(cudaMemsetAsync(errflag, 0, sizeof(int32_t), st));
+  if (nb > 0) {
+    ee_count_kernel<<<(unsigned)nb, EE_THREADS, 0, st>>>(src, dst, E, N, filter, blockcnt, errflag);
+    RGBMP_LAUNCH_CHECK("ee_count_kernel");
+    ee_save_last_kernel<<<1, 32, 0, st>>>(blockcnt, nb, last);
+    RGBMP_CUDA(exclusive_scan<int32_t>(blockcnt, nb, scanws, st));
+    ee_write_kernel<<<(unsigned)nb, EE_THREADS, 0, st>>>(src, dst, E, filter, blockcnt, e_src, e_dst);
+    RGBMP_LAUNCH_CHECK("ee_write_kernel");
+  } else {
+    RGBMP_CUDA(cudaMemsetAsync(last, 0, sizeof(int32_t), st));
+  }
+  const int64_t lb = ceil_div(N > 0 ? N : 1, 256);
+  ee_loops_kernel<<<(unsigned)lb, 256, 0, st>>>(N, add_loops, nb > 0 ? blockcnt : nullptr, nb, last, 0, e_src, e_dst,
+                                                nnz_dev, errflag);
+  RGBMP_LAUNCH_CHECK("ee_loops_kernel");
+  return 0;
+}
+
+size_t rgbmp_csr_build_workspace_bytes(int64_t nnz, int64_t N) {
+  (void)N;
+  const size_t n = (size_t)(nnz > 0 ? nnz : 1);
+  const size_t nb = (size_t)ceil_div((int64_t)n, RS_TILE);
+  size_t b = 0;
+  b += 3 * align_up(n * sizeof(int32_t), 256);                                    // keys A/B, vals A
+  b += align_up(RS_BINS * nb * sizeof(int32_t), 256);                              // block histograms
+  b += align_up(scan_ws_elems((int64_t)(RS_BINS * nb)) * sizeof(int32_t), 256);    // scan scratch (i32)
+  b += align_up(scan_ws_elems(N + 1) * sizeof(int64_t), 256);                      // scan scratch (i64)
+  return b + 4096;
+}
+
+int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64_t N, int64_t* rowptr, int32_t* col,
+                    int32_t* eid, void* ws, size_t ws_bytes, int device, void* stream) {
+  if (nnz < 0 || N < 0 || !rowptr || (nnz > 0 && (!key || !other || !col || !eid)) || !ws)
+    return fail(RGBMP_EINVAL, "rgbmp_csr_build: null pointer or negative size");
+  if (nnz >= (1ll << 31) - 1 || N >= (1ll << 31) - 1)
+    return fail(RGBMP_ERANGE, "rgbmp_csr_build: nnz=%lld or N=%lld exceeds int32", (long long)nnz, (long long)N);
+  if (ws_bytes < rgbmp_csr_build_workspace_bytes(nnz, N)) return fail(RGBMP_EWORKSPACE, "rgbmp_csr_build: workspace");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_csr_build: bad device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // rowptr = exclusive scan of the key histogram (int64)
+  RGBMP_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int64_t), st));
+  const size_t n = (size_t)(nnz > 0 ? nnz : 1);
+  const int64_t nb = ceil_div((int64_t)n, RS_TILE);
+  Carver cv(ws, ws_bytes);
+  int32_t* kA = cv.take<int32_t>(n);
+  int32_t* kB = cv.take<int32_t>(n);
+  int32_t* vA = cv.take<int32_t>(n);
+  int32_t* bh = cv.take<int32_t>((size_t)RS_BINS * nb);
+  int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
+  int64_t* sc64 = cv.take<int64_t>(scan_ws_elems(N + 1));
+  if (!cv.ok()) return fail(RGBMP_EWORKSPACE, "rgbmp_csr_build: workspace carve");
+  if (nnz > 0) {
+    deg_hist_kernel<<<kSMs * 8, 256, 0, st>>>(key, nnz, (unsigned long long*)rowptr);
+    RGBMP_LAUNCH_CHECK("deg_hist_kernel");
+  }
+  RGBMP_CUDA(exclusive_scan<int64_t>(rowptr, N + 1, sc64, st));
+  if (nnz == 0) return 0;
+
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < N) ++bits;
+  const int passes = (bits + 7) / 8;
+  // ping-pong so that the LAST pass writes values straight into `eid`; vals buffers: vA and eid
+  const int32_t* kin = key;
+  const int32_t* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    int32_t* kout = (p & 1) ? kB : kA;
+    // choose the value buffer so that pass (passes-1) lands in eid
+    int32_t* vout = (((passes - 1 - p) & 1) == 0) ? eid : vA;
+    rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, nnz, shift, nb, bh);
+    RGBMP_LAUNCH_CHECK("rs_hist_kernel");
+    RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
+    if (p == 0)
+      rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, nnz, shift, nb, bh, kout, vout);
+    else
+      rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, nnz, shift, nb, bh, kout, vout);
+    RGBMP_LAUNCH_CHECK("rs_scatter_kernel");
+    kin = kout;
+    vin = vout;
+  }
+  gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(other, eid, nnz, col);
+  RGBMP_LAUNCH_CHECK("gather_i32_kernel");
+  return 0;
+}
+
+int rgbmp_degree_norm(const int64_t* rowptr, int64_t N, int mode, float* out, int device, void* stream) {
+  if (!rowptr || !out || N < 0 || mode < 0 || mode > 2) return fail(RGBMP_EINVAL, "rgbmp_degree_norm: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_degree_norm: bad device");
+  if (N == 0) return 0;
+  degree_norm_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(rowptr, N, mode, out);
+  RGBMP_LAUNCH_CHECK("degree_norm_kernel");
+  return 0;
+}
+
+int rgbmp_gcn_edge_weight(const int64_t* rowptr, const int32_t* col, int64_t n_rows, const float* dinv_row,
+                          const float* dinv_col, float* val, int device, void* stream) {
+  if (!rowptr || !dinv_row || !dinv_col || n_rows < 0) return fail(RGBMP_EINVAL, "rgbmp_gcn_edge_weight: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_gcn_edge_weight: bad device");
+  if (n_rows == 0) return 0;
+  gcn_edge_weight_kernel<<<(unsigned)ceil_div(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      rowptr, col, n_rows, dinv_row, dinv_col, val);
+  RGBMP_LAUNCH_CHECK("gcn_edge_weight_kernel");
+  return 0;
+}
+
+int rgbmp_edge_permute(const float* in, const int32_t* eid, int64_t nnz, int H, int scatter, float* out, int device,
+                       void* stream) {
+  if (nnz < 0 || H <= 0 || (nnz > 0 && (!in || !eid || !out))) return fail(RGBMP_EINVAL, "rgbmp_edge_permute: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_edge_permute: bad device");
+  if (nnz == 0) return 0;
+  edge_permute_kernel<<<kSMs * 8, 256, 0, (cudaStream_t)stream>>>(in, eid, nnz, H, scatter, out);
+  RGBMP_LAUNCH_CHECK("edge_permute_kernel");
+  return 0;
+}
+
+int rgbmp_longrow_count(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk, int64_t* counts_dev,
+                        int device, void* stream) {
+  if (!rowptr || !counts_dev || n_rows < 0 || chunk <= 0 || long_chunk <= 0)
+    return fail(RGBMP_EINVAL, "rgbmp_longrow_count: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_longrow_count: bad device");
+  cudaStream_t st = (cudaStream_t)stream;
+  RGBMP_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(int64_t), st));
+  if (n_rows == 0) return 0;
+  longrow_count_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk,
+                                                                      (unsigned long long*)counts_dev);
+  RGBMP_LAUNCH_CHECK("longrow_count_kernel");
+  return 0;
+}
+
+size_t rgbmp_longrow_fill_workspace_bytes(int64_t n_rows) {
+  const size_t n = (size_t)(n_rows > 0 ? n_rows : 1);
+  return 2 * align_up(n * sizeof(int32_t), 256) + align_up(scan_ws_elems((int64_t)n) * sizeof(int32_t), 256) + 4096;
+}
+
+int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk, int64_t n_long,
+                       int64_t n_items, int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long,
+                       int64_t* item_start, void* ws, size_t ws_bytes, int device, void* stream) {
+  if (!rowptr || n_rows <= 0 || n_long <= 0 || n_items <= 0 || !long_rows || !long_item_ptr || !item_long ||
+      !item_start || !ws)
+    return fail(RGBMP_EINVAL, "rgbmp_longrow_fill: bad argument");
+  if (ws_bytes < rgbmp_longrow_fill_workspace_bytes(n_rows)) return fail(RGBMP_EWORKSPACE, "rgbmp_longrow_fill: workspace");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_longrow_fill: bad device");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(ws, ws_bytes);
+  int32_t* slot = cv.take<int32_t>((size_t)n_rows);
+  int32_t* items = cv.take<int32_t>((size_t)n_rows);
+  int32_t* sc = cv.take<int32_t>(scan_ws_elems(n_rows));
+  const unsigned nb = (unsigned)ceil_div(n_rows, 256);
+  longrow_flags_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, slot, items);
+  RGBMP_LAUNCH_CHECK("longrow_flags_kernel");
+  RGBMP_CUDA(exclusive_scan<int32_t>(slot, n_rows, sc, st));
+  RGBMP_CUDA(exclusive_scan<int32_t>(items, n_rows, sc, st));
+  longrow_fill_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, slot, items, n_long, n_items, long_rows,
+                                          long_item_ptr, item_long, item_start);
+  RGBMP_LAUNCH_CHECK("longrow_fill_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+// CSR SpMM host-side dispatch, K-hop driver, host-buffer entry point (sm_100a).
+#include "spmm_kernels.cuh"
+
+namespace rgbmp {
+
+// choose (G, V, U) for nvec vectors per row
+static void choose_shape(int nvec, int* G, int* V, int* U) {
+  if (nvec > 128) nvec = 128;  // wider rows are tiled over blockIdx.y
+  int bestG = 32, bestV = 4, bestWaste = 1 << 30;
+  const int Gs[6] = {32, 16, 8, 4, 2, 1};
+  for (int v = 1; v <= 4; ++v) {
+    for (int gi = 0; gi < 6; ++gi) {
+      const int g = Gs[gi];
+      if (g * v < nvec) continue;
+      const int waste = g * v - nvec;
+      // prefer no waste, then V<=2 (more rows per warp hurts less than idle lanes), then larger G
+      const int score = waste * 16 + (v > 2 ? 2 : 0) + (v == 1 ? 1 : 0);
+      if (score < bestWaste) { bestWaste = score; bestG = g; bestV = v; }
+    }
+  }
+  *G = bestG;
+  *V = bestV;
+  *U = 4;
+}
+
+static int check_graph(const rgbmp_graph_t* g, const char* fn) {
+  if (!g || !g->rowptr || g->n_rows < 0 || g->nnz < 0 || (g->nnz > 0 && !g->col))
+    return fail(RGBMP_EINVAL, "%s: bad graph descriptor", fn);
+  if (g->n_items > 0 && (!g->long_rows || !g->long_item_ptr || !g->item_long || !g->item_start || g->chunk <= 0 ||
+                         g->long_chunk <= 0))
+    return fail(RGBMP_EINVAL, "%s: incomplete long-row lists", fn);
+  if (g->n_cols >= (1ll << 31)) return fail(RGBMP_ERANGE, "%s: n_cols exceeds int32", fn);
+  return 0;
+}
+
+static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,
+                     int dtype, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SpmmParams p;
+  p.rowptr = g->rowptr;
+  p.col = g->col;
+  p.val = val;
+  p.n_rows = g->n_rows;
+  p.chunk = g->n_items > 0 ? g->chunk : 0;
+  p.long_chunk = g->long_chunk;
+  p.long_rows = g->long_rows;
+  p.long_item_ptr = g->long_item_ptr;
+  p.item_long = g->item_long;
+  p.item_start = g->item_start;
+  p.n_long = g->n_items > 0 ? g->n_long : 0;
+  p.n_items = g->n_items;
+  p.X = X;
+  p.ldx = ldx;
+  p.Y = Y;
+  p.ldy = ldy;
+  p.F = F;
+  if (ep) {
+    p.ep = *ep;
+  } else {
+    rgbmp_epilogue_t z = {};
+    z.a = 1.0f;
+    p.ep = z;
+  }
+  if (p.ep.reset_when != 0 && (!p.ep.reset_mask || !p.ep.reset_val))
+    return fail(RGBMP_EINVAL, "rgbmp_spmm: reset_when set without reset_mask/reset_val");
+  if (p.ep.Y2 && !p.ep.out2_scale) return fail(RGBMP_EINVAL, "rgbmp_spmm: Y2 without out2_scale");
+  if (!Y && !p.ep.Y2) return fail(RGBMP_EINVAL, "rgbmp_spmm: no output");
+
+  const int esz = dtype == RGBMP_BF16 ? 2 : 4;
+  const int epv_vec = 16 / esz;
+  auto aligned = [&](const void* ptr, int64_t ld) {
+    return ptr == nullptr || ((((uintptr_t)ptr) & 15) == 0 && (ld % epv_vec) == 0 && ld >= align_up(F, epv_vec));
+  };
+  const bool vec_ok = aligned(X, ldx) && aligned(Y, ldy) && aligned(p.ep.T, p.ep.ldt) && aligned(p.ep.Y2, p.ep.ldy2);
+  const int epv = vec_ok ? epv_vec : 1;
+  if (dtype == RGBMP_BF16 && !vec_ok)
+    return fail(RGBMP_EALIGN, "rgbmp_spmm: bf16 needs 16-byte aligned pointers and ld %% 8 == 0");
+
+  p.partial = nullptr;
+  p.ldpart = 0;
+  if (p.n_items > 0) {
+    p.ldpart = (int64_t)align_up(F, 4);
+    const size_t need = (size_t)p.n_items * p.ldpart * sizeof(float);
+    if (!ws || ws_bytes < need) return fail(RGBMP_EWORKSPACE, "rgbmp_spmm: workspace %zu < %zu", ws_bytes, need);
+    p.partial = (float*)ws;
+  }
+
+  int G, V, U;
+  const int nvec = (int)ceil_div(F, epv);
+  choose_shape(nvec, &G, &V, &U);
+  if (tune != 0) {
+    G = tune & 0xFF;
+    V = (tune >> 8) & 0xFF;
+    U = (tune >> 16) & 0xFF;
+    const bool pow2 = G > 0 && (G & (G - 1)) == 0 && G <= 32;
+    if (!pow2 || V < 1 || V > 4 || (U != 2 && U != 4 && U != 8))
+      return fail(RGBMP_EINVAL, "rgbmp_spmm: bad tune word 0x%x", tune);
+  }
+  if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(p, G, V, U, st);
+  if (epv == 4) return spmm_dispatch_f32v(p, G, V, U, st);
+  return spmm_dispatch_f32s(p, G, V, U, st);
+}
+
+}  // namespace rgbmp
+
+using namespace rgbmp;
+
+extern "C" {
+
+size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F) {
+  if (!g || g->n_items <= 0) return 256;
+  return (size_t)g->n_items * align_up((size_t)F, 4) * sizeof(float) + 256;
+}
+
+int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,
+               int dtype, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, int device, void* stream) {
+  int rc = check_graph(g, "rgbmp_spmm");
+  if (rc) return rc;
+  if (!X || F <= 0 || ldx < F || (Y && ldy < F)) return fail(RGBMP_EINVAL, "rgbmp_spmm: bad feature arguments");
+  if (dtype != RGBMP_F32 && dtype != RGBMP_BF16) return fail(RGBMP_EINVAL, "rgbmp_spmm: bad dtype %d", dtype);
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_spmm: bad device %d", device);
+  return spmm_impl(g, val, X, ldx, Y, ldy, F, dtype, ep, tune, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t ldx0, void* ping, void* pong,
+               int64_t ldp, void* out, int64_t ldo, void* hops, int64_t ld_hops, int64_t hop_stride, int F, int dtype,
+               int K, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, int device, void* stream) {
+  int rc = check_graph(g, "rgbmp_khop");
+  if (rc) return rc;
+  if (!X0 || (!out && !hops) || F <= 0 || K < 1 || ldx0 < F || (out && ldo < F))
+    return fail(RGBMP_EINVAL, "rgbmp_khop: bad arguments");
+  if (K > 1 && (!ping || !pong || ldp < F)) {
+    const bool through_hops = hops != nullptr && !(ep && ep->out2_scale);
+    if (!through_hops) return fail(RGBMP_EINVAL, "rgbmp_khop: K > 1 needs ping/pong buffers");
+  }
+  if (dtype != RGBMP_F32 && dtype != RGBMP_BF16) return fail(RGBMP_EINVAL, "rgbmp_khop: bad dtype %d", dtype);
+  if (g->n_rows != g->n_cols) return fail(RGBMP_EINVAL, "rgbmp_khop: needs a square graph");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_khop: bad device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = dtype == RGBMP_BF16 ? 2 : 4;
+  rgbmp_epilogue_t e;
+  if (ep) e = *ep;
+  else { e = rgbmp_epilogue_t{}; e.a = 1.0f; }
+  const bool folded = e.out2_scale != nullptr;  // iterate lives in the pre-scaled copy
+  const void* in = X0;
+  int64_t ldin = ldx0;
+  for (int k = 0; k < K; ++k) {
+    const bool last = (k == K - 1);
+    void* buf = (k & 1) ? pong : ping;
+    void* y = nullptr;
+    int64_t ldy = 0;
+    rgbmp_epilogue_t ek = e;
+    if (hops) { y = (char*)hops + (size_t)k * hop_stride * esz; ldy = ld_hops; }
+    if (last && !hops) { y = out; ldy = ldo; }
+    if (folded) {
+      ek.Y2 = last ? nullptr : buf;
+      ek.ldy2 = ldp;
+    } else {
+      ek.Y2 = nullptr;
+      if (!y) { y = buf; ldy = ldp; }
+    }
+    rc = spmm_impl(g, val, in, ldin, y, ldy, F, dtype, &ek, tune, ws, ws_bytes, st);
+    if (rc) return rc;
+    if (folded) { in = buf; ldin = ldp; }
+    else { in = y; ldin = ldy; }
+  }
+  if (hops && out) {  // final iterate also requested in `out`
+    const void* lastp = (const char*)hops + (size_t)(K - 1) * hop_stride * esz;
+    if (lastp != out)
+      RGBMP_CUDA(cudaMemcpy2DAsync(out, ldo * esz, lastp, ld_hops * esz, F * esz, g->n_rows, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, void* Y, int64_t ldy, int64_t n_rows,
+                    int F, int dtype, int device, void* stream) {
+  if (!X || !scale || !Y || n_rows < 0 || F <= 0 || ldx < F || ldy < F) return fail(RGBMP_EINVAL, "rgbmp_row_scale: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_row_scale: bad device");
+  if (n_rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == RGBMP_BF16)
+    row_scale_kernel<__nv_bfloat16><<<kSMs * 8, 256, 0, st>>>((const __nv_bfloat16*)X, ldx, scale, divide, (__nv_bfloat16*)Y, ldy, n_rows, F);
+  else
+    row_scale_kernel<float><<<kSMs * 8, 256, 0, st>>>((const float*)X, ldx, scale, divide, (float*)Y, ldy, n_rows, F);
+  RGBMP_LAUNCH_CHECK("row_scale_kernel");
+  return 0;
+}
+
+int rgbmp_appnp_host(const rgbmp_graph_t* g, const float* dinv, const float* z0_host, float* out_host, int F, int K,
+                     float alpha, float* dev_z0, float* dev_ping, float* dev_pong, float* dev_out, int64_t ld, void* ws,
+                     size_t ws_bytes, int device, void* stream) {
+  int rc = check_graph(g, "rgbmp_appnp_host");
+  if (rc) return rc;
+  if (!dinv || !z0_host || !out_host || !dev_z0 || !dev_ping || !dev_pong || !dev_out || F <= 0 || K < 1 || ld < F)
+    return fail(RGBMP_EINVAL, "rgbmp_appnp_host: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_appnp_host: bad device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = g->n_rows;
+  RGBMP_CUDA(cudaMemcpy2DAsync(dev_z0, ld * sizeof(float), z0_host, F * sizeof(float), F * sizeof(float), N,
+                               cudaMemcpyHostToDevice, st));
+  // u0 = D^-1/2 z0 (into pong, which hop 1 reads; hop 1 writes ping)
+  rc = rgbmp_row_scale(dev_z0, ld, dinv, 0, dev_pong, ld, N, F, RGBMP_F32, device, stream);
+  if (rc) return rc;
+  rgbmp_epilogue_t e = {};
+  e.row_scale = dinv;
+  e.a = 1.0f - alpha;
+  e.b = alpha;
+  e.T = dev_z0;
+  e.ldt = ld;
+  e.out2_scale = dinv;
+  // hop k writes (k odd ? pong : ping); the first hop reads pong, so start the ping/pong at ping
+  rc = rgbmp_khop(g, nullptr, dev_pong, ld, dev_ping, dev_pong, ld, dev_out, ld, nullptr, 0, 0, F, RGBMP_F32, K, &e, 0, ws,
+                  ws_bytes, device, stream);
+  if (rc) return rc;
+  RGBMP_CUDA(cudaMemcpy2DAsync(out_host, F * sizeof(float), dev_out, ld * sizeof(float), F * sizeof(float), N,
+                               cudaMemcpyDeviceToHost, st));
+  RGBMP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

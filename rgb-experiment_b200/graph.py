@@ -1,0 +1,231 @@
+"""Device-resident graph objects built by the integer CUDA kernels, and their cache.
+
+PyG keeps graphs in COO and re-runs ``gcn_norm`` (self-loop concat + degree scatter + two
+gathers) on every forward of every layer, three times per epoch.  Here the edge
+list is edited and sorted ONCE into a CSR over targets (forward aggregation) and, lazily, a CSR
+over sources (backward), cached on the identity of the ``edge_index`` tensor that reaches the
+layers (stable across epochs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GraphStruct, check, lib, ptr, stream_of
+
+LOOP_NONE, LOOP_ADD, LOOP_ADD_REMAINING, LOOP_REMOVE_THEN_ADD = 0, 1, 2, 3
+NORM_INV_SQRT, NORM_INV_MEAN, NORM_COUNT = 0, 1, 2
+
+DEFAULT_CHUNK = 1024        # rows with more edges than this are split ...
+DEFAULT_LONG_CHUNK = 4096   # ... into CTA work items of this many edges
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class CSR:
+    """One orientation of the graph: rowptr int64 [n_rows+1], col int32 [nnz], eid int32 [nnz]
+    (position in the edited edge list), plus the long-row work lists and the ctypes descriptor."""
+
+    def __init__(self, key: torch.Tensor, other: torch.Tensor, n_rows: int, n_cols: int,
+                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK):
+        L = lib()
+        dev = key.device
+        st = stream_of(dev)
+        nnz = key.numel()
+        self.n_rows, self.n_cols, self.nnz, self.device = n_rows, n_cols, nnz, dev
+        self.rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        self.col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        self.eid = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        wsb = L.rgbmp_csr_build_workspace_bytes(nnz, n_rows)
+        ws = _ws(wsb, dev)
+        check(L.rgbmp_csr_build(ptr(key), ptr(other), nnz, n_rows, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
+                                ptr(ws), ws.numel(), dev.index, st), "csr_build")
+        self.col, self.eid = self.col[:nnz], self.eid[:nnz]
+        self.chunk, self.long_chunk = int(chunk), int(long_chunk)
+        self.n_long = self.n_items = 0
+        self.long_rows = self.long_item_ptr = self.item_long = self.item_start = None
+        self._split_long_rows()
+        self._norm = {}
+        self.struct = GraphStruct(n_rows, n_cols, nnz, ptr(self.rowptr), ptr(self.col), self.chunk, self.long_chunk,
+                                  self.n_long, self.n_items, ptr(self.long_rows), ptr(self.long_item_ptr),
+                                  ptr(self.item_long), ptr(self.item_start))
+        self.ref = C.byref(self.struct)
+
+    def _split_long_rows(self):
+        L = lib()
+        dev, st = self.device, stream_of(self.device)
+        if self.n_rows == 0 or self.nnz == 0:
+            return
+        counts = torch.empty(2, dtype=torch.int64, device=dev)
+        check(L.rgbmp_longrow_count(ptr(self.rowptr), self.n_rows, self.chunk, self.long_chunk, ptr(counts),
+                                    dev.index, st), "longrow_count")
+        n_long, n_items = (int(v) for v in counts.tolist())       # one sync at build time
+        if n_long == 0:
+            return
+        self.n_long, self.n_items = n_long, n_items
+        self.long_rows = torch.empty(n_long, dtype=torch.int32, device=dev)
+        self.long_item_ptr = torch.empty(n_long + 1, dtype=torch.int32, device=dev)
+        self.item_long = torch.empty(n_items, dtype=torch.int32, device=dev)
+        self.item_start = torch.empty(n_items, dtype=torch.int64, device=dev)
+        ws = _ws(L.rgbmp_longrow_fill_workspace_bytes(self.n_rows), dev)
+        check(L.rgbmp_longrow_fill(ptr(self.rowptr), self.n_rows, self.chunk, self.long_chunk, n_long, n_items,
+                                   ptr(self.long_rows), ptr(self.long_item_ptr), ptr(self.item_long),
+                                   ptr(self.item_start), ptr(ws), ws.numel(), dev.index, st), "longrow_fill")
+
+    def norm(self, mode: int) -> torch.Tensor:
+        """Per-row vector from the degree: deg^-1/2 | 1/max(deg,1) | max(deg,1)."""
+        v = self._norm.get(mode)
+        if v is None:
+            v = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            check(lib().rgbmp_degree_norm(ptr(self.rowptr), self.n_rows, mode, ptr(v), self.device.index,
+                                          stream_of(self.device)), "degree_norm")
+            self._norm[mode] = v
+        return v
+
+    def degree(self) -> torch.Tensor:
+        return self.rowptr[1:] - self.rowptr[:-1]
+
+    def spmm_workspace(self, F: int) -> Optional[torch.Tensor]:
+        if self.n_items == 0:
+            return None
+        return _ws(self.n_items * ((F + 3) // 4 * 4) * 4 + 256, self.device)
+
+
+class Graph:
+    """Edited edge list + forward CSR (+ lazy transpose CSR, normalisation vectors, edge weights)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, loop_mode: int = LOOP_NONE,
+                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK):
+        _lib.require_cuda(edge_index, "edge_index")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
+        L = lib()
+        dev = edge_index.device
+        st = stream_of(dev)
+        ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+        E, N = ei.size(1), int(num_nodes)
+        self.N, self.E_in, self.loop_mode, self.device = N, E, loop_mode, dev
+        self._chunk, self._long_chunk = chunk, long_chunk
+        e_src = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+        e_dst = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+        nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+        ws = _ws(L.rgbmp_edge_edit_workspace_bytes(E, N), dev)
+        check(L.rgbmp_edge_edit(ptr(ei[0]) if E else None, ptr(ei[1]) if E else None, E, N, loop_mode, ptr(e_src),
+                                ptr(e_dst), ptr(nnz_dev), ptr(ws), ws.numel(), dev.index, st), "edge_edit")
+        nnz = int(nnz_dev.item())                                  # the one sync of the build
+        if nnz < 0:
+            raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
+        self.nnz = nnz
+        self.e_src, self.e_dst = e_src[:nnz], e_dst[:nnz]          # edited list: kept edges, then loops
+        self.fwd = CSR(self.e_dst, self.e_src, N, N, chunk, long_chunk)   # rows = targets i, col = sources j
+        self._bwd: Optional[CSR] = None
+        self._lock = threading.Lock()
+        self._vals = {}
+
+    # transpose CSR: rows = sources j, col = targets i (built on first backward)
+    @property
+    def bwd(self) -> CSR:
+        if self._bwd is None:
+            with self._lock:
+                if self._bwd is None:
+                    self._bwd = CSR(self.e_src, self.e_dst, self.N, self.N, self._chunk, self._long_chunk)
+        return self._bwd
+
+    def dinv(self) -> torch.Tensor:
+        """deg_in^-1/2 with inf -> 0 (gcn_norm, dagnn.py:27-30; unit edge weights)."""
+        return self.fwd.norm(NORM_INV_SQRT)
+
+    def gcn_val(self, transpose: bool = False) -> torch.Tensor:
+        """Per-edge symmetric weights dinv[src]*1*dinv[dst] in the CSR order of the chosen orientation."""
+        key = ("gcn", transpose)
+        v = self._vals.get(key)
+        if v is None:
+            csr = self.bwd if transpose else self.fwd
+            d = self.dinv()
+            v = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.device)
+            check(lib().rgbmp_gcn_edge_weight(ptr(csr.rowptr), ptr(csr.col), csr.n_rows, ptr(d), ptr(d), ptr(v),
+                                              self.device.index, stream_of(self.device)), "gcn_edge_weight")
+            v = v[:self.nnz]
+            self._vals[key] = v
+        return v
+
+    def tpos(self) -> torch.Tensor:
+        """int32 [nnz]: forward-CSR position of every transpose-CSR entry."""
+        v = self._vals.get("tpos")
+        if v is None:
+            inv = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            inv[self.fwd.eid.long()] = torch.arange(self.nnz, dtype=torch.int32, device=self.device)
+            v = inv[self.bwd.eid.long()].contiguous()
+            self._vals["tpos"] = v
+        return v
+
+    def fwd_to_bwd(self, csr_vals: torch.Tensor) -> torch.Tensor:
+        """[nnz(,H)] values in forward-CSR order -> transpose-CSR order."""
+        return csr_vals[self.tpos().long()].contiguous()
+
+    def edge_index(self) -> torch.Tensor:
+        """The edited edge list as an int64 [2, nnz] tensor (what PyG's loop utilities return)."""
+        v = self._vals.get("edge_index")
+        if v is None:
+            v = torch.stack([self.e_src, self.e_dst]).to(torch.int64)
+            self._vals["edge_index"] = v
+        return v
+
+    def to_csr_order(self, edge_vals: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        """edge-ordered [nnz] or [nnz,H] float32 -> CSR order of the chosen orientation."""
+        csr = self.bwd if transpose else self.fwd
+        ev = edge_vals.contiguous().to(torch.float32)
+        H = 1 if ev.dim() == 1 else ev.size(1)
+        out = torch.empty_like(ev)
+        check(lib().rgbmp_edge_permute(ptr(ev), ptr(csr.eid), self.nnz, H, 0, ptr(out), self.device.index,
+                                       stream_of(self.device)), "edge_permute")
+        return out
+
+    def to_edge_order(self, csr_vals: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        csr = self.bwd if transpose else self.fwd
+        cv = csr_vals.contiguous()
+        H = 1 if cv.dim() == 1 else cv.size(1)
+        out = torch.empty_like(cv)
+        check(lib().rgbmp_edge_permute(ptr(cv), ptr(csr.eid), self.nnz, H, 1, ptr(out), self.device.index,
+                                       stream_of(self.device)), "edge_permute")
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# cache keyed on the identity of the edge_index tensor that reaches the layers
+# --------------------------------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_LOCK = threading.Lock()
+_CACHE_MAX = 16
+stats = {"hits": 0, "builds": 0}
+
+
+def get_graph(edge_index: torch.Tensor, num_nodes: int, loop_mode: int) -> Graph:
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
+           int(num_nodes), int(loop_mode), str(edge_index.device))
+    with _CACHE_LOCK:
+        hit = _CACHE.get(key)
+        if hit is not None:
+            _CACHE.move_to_end(key)
+            stats["hits"] += 1
+            return hit[0]
+    g = Graph(edge_index, num_nodes, loop_mode)
+    with _CACHE_LOCK:
+        # keep a reference to the tensor so that its storage (and therefore the key) stays unique
+        _CACHE[key] = (g, edge_index)
+        stats["builds"] += 1
+        while len(_CACHE) > _CACHE_MAX:
+            _CACHE.popitem(last=False)
+    return g
+
+
+def clear_cache():
+    with _CACHE_LOCK:
+        _CACHE.clear()

@@ -1,0 +1,560 @@
+"""torch.autograd.Function drop-ins over the C ABI (include/rgbmp.h).
+
+Every function here enqueues hand-written sm_100a kernels from librgbmp.so on the current
+CUDA stream.  Nothing falls back to PyTorch arithmetic for the aggregation itself; PyTorch only
+provides the tensors (device memory), the stream and the autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check, dtype_code, lib, ptr, stream_of
+from .graph import CSR, Graph, NORM_COUNT, NORM_INV_SQRT
+
+RESET_NONE, RESET_BEFORE_TELEPORT, RESET_AFTER_CLAMP = 0, 1, 2
+
+
+# ------------------------------------------------------------------------------------------
+# buffer helpers: the vector path wants 16-byte aligned rows (ld % 4 == 0 fp32, % 8 bf16)
+# ------------------------------------------------------------------------------------------
+def _vec(dtype) -> int:
+    return 8 if dtype == torch.bfloat16 else 4
+
+
+def padded_width(F: int, dtype=torch.float32) -> int:
+    v = _vec(dtype)
+    return (F + v - 1) // v * v
+
+
+def as_rows(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """Return (tensor usable by the kernels, leading dimension).  No copy when `x` is already
+    row-major with an aligned row stride; otherwise one copy into a zero-padded buffer."""
+    _lib.require_cuda(x, "x")
+    if x.dim() != 2:
+        raise RuntimeError("feature matrix must be 2-D [rows, F]")
+    N, F = x.shape
+    v = _vec(x.dtype)
+    if (x.stride(1) == 1 or F == 1) and x.stride(0) % v == 0 and x.stride(0) >= padded_width(F, x.dtype) \
+            and x.data_ptr() % 16 == 0:
+        return x, x.stride(0)
+    Fp = padded_width(F, x.dtype)
+    if Fp == F:
+        buf = x.contiguous()
+        if buf.data_ptr() % 16 == 0:
+            return buf, F
+    buf = torch.zeros((N, Fp), dtype=x.dtype, device=x.device)
+    buf[:, :F].copy_(x)
+    return buf[:, :F], Fp
+
+
+def alloc_rows(N: int, F: int, dtype, device) -> Tuple[torch.Tensor, int]:
+    """[N, F] view of a fresh [N, padded(F)] buffer."""
+    Fp = padded_width(F, dtype)
+    buf = torch.empty((N, Fp), dtype=dtype, device=device)
+    return (buf if Fp == F else buf[:, :F]), Fp
+
+
+def make_epilogue(*, row_scale=None, row_div=False, a=1.0, b=0.0, T=None, ldt=0, clamp=None,
+                  reset_mask=None, reset_val=None, ld_reset=0, reset_when=RESET_NONE,
+                  out2_scale=None) -> Epilogue:
+    e = Epilogue()
+    e.row_scale, e.row_div = ptr(row_scale), int(bool(row_div))
+    e.reset_mask, e.reset_val, e.ld_reset, e.reset_when = ptr(reset_mask), ptr(reset_val), ld_reset, reset_when
+    e.a, e.b, e.T, e.ldt = float(a), float(b), ptr(T), ldt
+    if clamp is not None:
+        e.clamp, e.lo, e.hi = 1, float(clamp[0]), float(clamp[1])
+    e.out2_scale = ptr(out2_scale)
+    return e
+
+
+def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, ep: Optional[Epilogue] = None,
+             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[i] = epilogue(sum_k val[k] * x[col[k]]).  `keep` holds tensors referenced by `ep`."""
+    xb, ldx = as_rows(x)
+    F = x.size(1)
+    if x.size(0) < csr.n_cols:
+        raise RuntimeError(f"x has {x.size(0)} rows but the graph addresses {csr.n_cols}")
+    if out is None:
+        y, ldy = alloc_rows(csr.n_rows, F, x.dtype, x.device)
+    else:
+        y, ldy = out, out.stride(0)
+    ws = csr.spmm_workspace(F)
+    dev = x.device
+    check(lib().rgbmp_spmm(csr.ref, ptr(val), ptr(xb), ldx, ptr(y), ldy, F, dtype_code(x),
+                           C.byref(ep) if ep is not None else None, tune, ptr(ws),
+                           0 if ws is None else ws.numel(), dev.index, stream_of(dev)), "spmm")
+    return y
+
+
+def row_scale(x: torch.Tensor, scale: torch.Tensor, divide: bool = False) -> torch.Tensor:
+    xb, ldx = as_rows(x)
+    y, ldy = alloc_rows(x.size(0), x.size(1), x.dtype, x.device)
+    dev = x.device
+    check(lib().rgbmp_row_scale(ptr(xb), ldx, ptr(scale), int(divide), ptr(y), ldy, x.size(0), x.size(1),
+                                dtype_code(x), dev.index, stream_of(dev)), "row_scale")
+    return y
+
+
+def khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilogue] = None, keep=(),
+             hops: bool = False, tune: int = 0):
+    """K fused hops.  Returns the final iterate, or (final, [K, N, F] hop outputs) when hops=True."""
+    xb, ldx = as_rows(x0)
+    N, F = x0.shape
+    dev, dt = x0.device, x0.dtype
+    Fp = padded_width(F, dt)
+    out, ldo = alloc_rows(N, F, dt, dev)
+    ping = pong = None
+    if K > 1:
+        ping = torch.empty((N, Fp), dtype=dt, device=dev)
+        pong = torch.empty((N, Fp), dtype=dt, device=dev)
+    hop_buf = torch.empty((K, N, Fp), dtype=dt, device=dev) if hops else None
+    ws = csr.spmm_workspace(F)
+    check(lib().rgbmp_khop(csr.ref, ptr(val), ptr(xb), ldx, ptr(ping), ptr(pong), Fp, ptr(out), ldo,
+                           ptr(hop_buf), Fp, N * Fp, F, dtype_code(x0), K,
+                           C.byref(ep) if ep is not None else None, tune, ptr(ws),
+                           0 if ws is None else ws.numel(), dev.index, stream_of(dev)), "khop")
+    if hops:
+        return out, hop_buf[:, :, :F]
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# single-hop propagate  (MessagePassing.propagate / GCNConv / SAGEConv / GINConv ...)
+# ------------------------------------------------------------------------------------------
+class _Propagate(torch.autograd.Function):
+    """kind: 'sum' (aggr='add', message=x_j), 'mean' (aggr='mean'), 'gcn' (symmetric norm weights).
+    Backward = the same kernel on the transpose CSR (linear operator, nothing but the graph saved)."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, kind: str):
+        ctx.graph, ctx.kind = graph, kind
+        csr = graph.fwd
+        if kind == "sum":
+            return spmm_raw(csr, x)
+        if kind == "mean":
+            cnt = csr.norm(NORM_COUNT)
+            return spmm_raw(csr, x, ep=make_epilogue(row_scale=cnt, row_div=True), keep=(cnt,))
+        if kind == "gcn":
+            return spmm_raw(csr, x, graph.gcn_val(False))
+        raise ValueError(kind)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g, kind = ctx.graph, ctx.kind
+        if kind == "sum":
+            return spmm_raw(g.bwd, dy), None, None
+        if kind == "mean":
+            return spmm_raw(g.bwd, row_scale(dy, g.fwd.norm(NORM_COUNT), divide=True)), None, None
+        return spmm_raw(g.bwd, dy, g.gcn_val(True)), None, None
+
+
+def propagate(x: torch.Tensor, graph: Graph, kind: str = "sum") -> torch.Tensor:
+    return _Propagate.apply(x, graph, kind)
+
+
+class _PropagateWeighted(torch.autograd.Function):
+    """y[i] = sum_{e: dst=i} w[e] * x[src[e]] with per-edge weights given in EDGE order [nnz]
+    (Prop.message, dagnn.py:57-59; generic edge_weight).  dw[e] = <dy[dst], x[src]> (SDDMM)."""
+
+    @staticmethod
+    def forward(ctx, x, w, graph: Graph):
+        ctx.graph = graph
+        val = graph.to_csr_order(w, transpose=False)
+        ctx.save_for_backward(x if ctx.needs_input_grad[1] else None, w)
+        return spmm_raw(graph.fwd, x, val)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.graph
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = spmm_raw(g.bwd, dy, g.to_csr_order(w, transpose=True))
+        if ctx.needs_input_grad[1]:
+            dw = g.to_edge_order(sddmm(g.fwd, dy, x, 1, dy.size(1))).view_as(w)
+        return dx, dw, None
+
+
+def propagate_weighted(x, w, graph: Graph):
+    return _PropagateWeighted.apply(x, w, graph)
+
+
+# ------------------------------------------------------------------------------------------
+# K-hop families
+# ------------------------------------------------------------------------------------------
+def _appnp_khop(csr: CSR, graph: Graph, x: torch.Tensor, K: int, alpha: float, transpose: bool, fold: bool):
+    xb, ldx = as_rows(x)
+    if fold:
+        d = graph.dinv()
+        u0 = row_scale(xb, d)
+        ep = make_epilogue(row_scale=d, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx, out2_scale=d)
+        return khop_raw(csr, u0, K, ep=ep, keep=(d, xb))
+    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
+    return khop_raw(csr, xb, K, val=graph.gcn_val(transpose), ep=ep, keep=(xb,))
+
+
+class _APPNP(torch.autograd.Function):
+    """z = x; K x { z = (1-alpha) * A_hat z + alpha * x }  (A8; appnp_stack.py:22).
+    The map is linear, z_K = M x with M = alpha*sum_{k<K} B^k + B^K, B=(1-alpha)A_hat, so the
+    backward is the same recursion on the transpose graph -- no hop activations are kept."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, K: int, alpha: float, fold: bool):
+        ctx.graph, ctx.K, ctx.alpha, ctx.fold = graph, K, alpha, fold
+        return _appnp_khop(graph.fwd, graph, x, K, alpha, False, fold)
+
+    @staticmethod
+    def backward(ctx, dz):
+        g = ctx.graph
+        return _appnp_khop(g.bwd, g, dz, ctx.K, ctx.alpha, True, ctx.fold), None, None, None, None
+
+
+def appnp(x, graph: Graph, K: int, alpha: float, fold: bool = False):
+    if K == 0:
+        return x
+    return _APPNP.apply(x, graph, int(K), float(alpha), bool(fold))
+
+
+class _PowerHops(torch.autograd.Function):
+    """x <- A_hat^K x (A9 SGConv, sgc.py:9-10)."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, K: int):
+        ctx.graph, ctx.K = graph, K
+        return khop_raw(graph.fwd, x, K, val=graph.gcn_val(False))
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.graph
+        return khop_raw(g.bwd, dy, ctx.K, val=g.gcn_val(True)), None, None
+
+
+def gcn_power(x, graph: Graph, K: int):
+    return x if K == 0 else _PowerHops.apply(x, graph, int(K))
+
+
+def dagnn_hops(x: torch.Tensor, graph: Graph, K: int) -> torch.Tensor:
+    """[N, K+1, C] stack of x and its K propagated versions (dagnn.py:43-49), forward only."""
+    _, hops = khop_raw(graph.fwd, x, K, val=graph.gcn_val(False), hops=True)
+    return torch.cat([x.unsqueeze(0), hops], dim=0).permute(1, 0, 2)
+
+
+def label_propagation(graph: Graph, out0: torch.Tensor, num_layers: int, alpha: float, *,
+                      clamp=(0.0, 1.0), reset_mask=None, reset_val=None) -> torch.Tensor:
+    """A15 LP core: res=(1-a)*out0; L x { out = a * A_hat out + res; post_step }.
+    post_step = clamp(lo,hi) (default / autoscale) or `out[mask] = reset_val[mask]` (fixed scale).
+    `graph` must be built with LOOP_NONE (gcn_norm(add_self_loops=False))."""
+    if num_layers == 0:
+        return out0
+    xb, ldx = as_rows(out0)
+    kw = {}
+    keep = [xb]
+    if reset_mask is not None:
+        m = reset_mask.to(torch.uint8).contiguous()
+        rv, ldr = as_rows(reset_val)
+        kw = dict(reset_mask=m, reset_val=rv, ld_reset=ldr, reset_when=RESET_AFTER_CLAMP)
+        keep += [m, rv]
+        clamp = None
+    ep = make_epilogue(a=alpha, b=1.0 - alpha, T=xb, ldt=ldx, clamp=clamp, **kw)
+    return khop_raw(graph.fwd, xb, num_layers, val=graph.gcn_val(False), ep=ep, keep=keep)
+
+
+# ------------------------------------------------------------------------------------------
+# PTA graph ops (itexperiments.py:671-719, pta.py:79-84).  The PTA adjacency aggregates at
+# row = edge_index[0], i.e. it is the gcn propagation of the REVERSED graph, with A+I doubling
+# an existing self loop -> build the graph with LOOP_ADD on the flipped
+# edge_index: duplicates and pre-existing loops then count exactly like the scipy COO sum.
+# ------------------------------------------------------------------------------------------
+def pta_graph(edge_index: torch.Tensor, num_nodes: int) -> Graph:
+    from .graph import LOOP_ADD, get_graph
+    return get_graph(edge_index.flip(0).contiguous(), num_nodes, LOOP_ADD)
+
+
+def pta_inference(h: torch.Tensor, graph: Graph, K: int, alpha: float) -> torch.Tensor:
+    y0 = torch.softmax(h, dim=-1)
+    xb, ldx = as_rows(y0)
+    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
+    return khop_raw(graph.fwd, xb, K, val=graph.gcn_val(False), ep=ep, keep=(xb,))
+
+
+def pta_label_propagation(graph: Graph, labels: torch.Tensor, idx: torch.Tensor, K: int, alpha: float):
+    N = labels.size(0)
+    Cn = int(labels.max().item()) + 1
+    y0 = torch.zeros((N, Cn), dtype=torch.float32, device=labels.device)
+    y0[idx, labels[idx]] = 1.0
+    mask = torch.zeros(N, dtype=torch.uint8, device=labels.device)
+    mask[idx] = 1
+    xb, ldx = as_rows(y0)
+    # y <- A y ; y[idx] <- onehot[idx] (= y0[idx]) ; y <- (1-a) y + a y0
+    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx, reset_mask=mask, reset_val=xb, ld_reset=ldx,
+                       reset_when=RESET_BEFORE_TELEPORT)
+    return khop_raw(graph.fwd, xb, K, val=graph.gcn_val(False), ep=ep, keep=(xb, mask))
+
+
+# ------------------------------------------------------------------------------------------
+# attention / edge-score kernels
+# ------------------------------------------------------------------------------------------
+def sddmm(csr: CSR, A: torch.Tensor, B: torch.Tensor, H: int, Cc: int) -> torch.Tensor:
+    """out[k,h] = <A[row_i,h,:], B[col[k],h,:]> in CSR order."""
+    Ab, lda = as_rows(A)
+    Bb, ldb = as_rows(B)
+    out = torch.empty((csr.nnz, H), dtype=torch.float32, device=A.device)
+    dev = A.device
+    check(lib().rgbmp_sddmm(csr.ref, ptr(Ab), lda, ptr(Bb), ldb, H, Cc, ptr(out), dev.index, stream_of(dev)), "sddmm")
+    return out
+
+
+def _edge_call(fn_name, csr: CSR, *args):
+    dev = csr.device
+    check(getattr(lib(), fn_name)(csr.ref, *args, dev.index, stream_of(dev)), fn_name)
+
+
+def spmm_heads_raw(csr: CSR, w: torch.Tensor, X: torch.Tensor, H: int, Cc: int) -> torch.Tensor:
+    Xb, ldx = as_rows(X)
+    out, ldo = alloc_rows(csr.n_rows, H * Cc, torch.float32, X.device)
+    _edge_call("rgbmp_spmm_heads", csr, ptr(w.contiguous()), ptr(Xb), ldx, H, Cc, ptr(out), ldo)
+    return out
+
+
+def seg_sum_raw(csr: CSR, vals: torch.Tensor, H: int) -> torch.Tensor:
+    out = torch.empty((csr.n_rows, H), dtype=torch.float32, device=vals.device)
+    _edge_call("rgbmp_seg_sum", csr, ptr(vals.contiguous()), H, ptr(out))
+    return out
+
+
+class _SDDMM(torch.autograd.Function):
+    """out[k,h] = <A[i,h,:], B[j,h,:]> for every edge j->i, forward-CSR order (SuperGAT MX logits)."""
+
+    @staticmethod
+    def forward(ctx, A, B, graph: Graph, H: int, Cc: int):
+        ctx.graph, ctx.H, ctx.Cc = graph, H, Cc
+        ctx.save_for_backward(A, B)
+        return sddmm(graph.fwd, A, B, H, Cc)
+
+    @staticmethod
+    def backward(ctx, g):
+        A, B = ctx.saved_tensors
+        gr, H, Cc = ctx.graph, ctx.H, ctx.Cc
+        g = g.contiguous()
+        dA = spmm_heads_raw(gr.fwd, g, B, H, Cc) if ctx.needs_input_grad[0] else None
+        dB = spmm_heads_raw(gr.bwd, gr.fwd_to_bwd(g), A, H, Cc) if ctx.needs_input_grad[1] else None
+        return dA, dB, None, None, None
+
+
+class _UAddV(torch.autograd.Function):
+    """out[k,h] = u[j,h] + v[i,h] for every edge j->i (forward-CSR order)."""
+
+    @staticmethod
+    def forward(ctx, u, v, graph: Graph):
+        ctx.graph = graph
+        H = u.size(1)
+        out = torch.empty((graph.nnz, H), dtype=torch.float32, device=u.device)
+        _edge_call("rgbmp_u_add_v", graph.fwd, ptr(u.contiguous()), ptr(v.contiguous()), H, ptr(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gr = ctx.graph
+        g = g.contiguous()
+        H = g.size(1)
+        du = seg_sum_raw(gr.bwd, gr.fwd_to_bwd(g), H) if ctx.needs_input_grad[0] else None
+        dv = seg_sum_raw(gr.fwd, g, H) if ctx.needs_input_grad[1] else None
+        return du, dv, None
+
+
+class _SegSoftmax(torch.autograd.Function):
+    """Edge softmax over the in-edges of each target (A11), forward-CSR order."""
+
+    @staticmethod
+    def forward(ctx, e, graph: Graph):
+        ctx.graph = graph
+        e = e.contiguous()
+        out = torch.empty_like(e)
+        _edge_call("rgbmp_seg_softmax", graph.fwd, ptr(e), e.size(1), ptr(out))
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (alpha,) = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        _edge_call("rgbmp_seg_softmax_backward", ctx.graph.fwd, ptr(alpha), ptr(g), g.size(1), ptr(out))
+        return out, None
+
+
+class _SpmmHeads(torch.autograd.Function):
+    """out[i,h,:] = sum_{j->i} w[k,h] * X[j,h,:], w in forward-CSR order."""
+
+    @staticmethod
+    def forward(ctx, w, X, graph: Graph, H: int, Cc: int):
+        ctx.graph, ctx.H, ctx.Cc = graph, H, Cc
+        ctx.save_for_backward(w, X)
+        return spmm_heads_raw(graph.fwd, w, X, H, Cc)
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, X = ctx.saved_tensors
+        gr, H, Cc = ctx.graph, ctx.H, ctx.Cc
+        dw = sddmm(gr.fwd, dout, X, H, Cc) if ctx.needs_input_grad[0] else None
+        dX = spmm_heads_raw(gr.bwd, gr.fwd_to_bwd(w), dout, H, Cc) if ctx.needs_input_grad[1] else None
+        return dw, dX, None, None, None
+
+
+def edge_sddmm(A, B, graph, H, Cc):
+    return _SDDMM.apply(A, B, graph, H, Cc)
+
+
+def edge_u_add_v(u, v, graph):
+    return _UAddV.apply(u, v, graph)
+
+
+def edge_softmax(e, graph):
+    return _SegSoftmax.apply(e, graph)
+
+
+def spmm_heads(w, X, graph, H, Cc):
+    return _SpmmHeads.apply(w, X, graph, H, Cc)
+
+
+def gat_fusable(H: int, Cc: int) -> bool:
+    if H * Cc > 128:
+        return False
+    if H == 1:
+        return True
+    q = Cc // 4
+    return Cc % 4 == 0 and q > 0 and (q & (q - 1)) == 0
+
+
+class _GAT(torch.autograd.Function):
+    """Fused GATConv attention + aggregate (A10/A11; gat.py:18-21).  Saves only the per-node
+    softmax statistics (max, sum) [N,H]; alpha is recomputed in the backward."""
+
+    @staticmethod
+    def forward(ctx, xp, a_src, a_dst, graph: Graph, H: int, Cc: int, slope: float, drop_csr):
+        xb, ldx = as_rows(xp)
+        a_s, a_d = a_src.contiguous(), a_dst.contiguous()
+        N = graph.N
+        out, ldo = alloc_rows(N, H * Cc, torch.float32, xp.device)
+        rmax = torch.empty((N, H), dtype=torch.float32, device=xp.device)
+        rsum = torch.empty((N, H), dtype=torch.float32, device=xp.device)
+        dev = xp.device
+        check(lib().rgbmp_gat_forward(graph.fwd.ref, ptr(xb), ldx, ptr(a_s), ptr(a_d), H, Cc, slope, ptr(drop_csr),
+                                      ptr(out), ldo, ptr(rmax), ptr(rsum), None, 0, dev.index, stream_of(dev)),
+              "gat_forward")
+        ctx.graph, ctx.H, ctx.Cc, ctx.slope = graph, H, Cc, slope
+        ctx.save_for_backward(xb, a_s, a_d, rmax, rsum, out, drop_csr)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xb, a_s, a_d, rmax, rsum, out, drop = ctx.saved_tensors
+        g, H, Cc = ctx.graph, ctx.H, ctx.Cc
+        dev = dout.device
+        db, ldd = as_rows(dout)
+        N = g.N
+        S = torch.empty((N, H), dtype=torch.float32, device=dev)
+        check(lib().rgbmp_rowdot(ptr(db), ldd, ptr(out), out.stride(0), N, H, Cc, ptr(S), dev.index, stream_of(dev)),
+              "rowdot")
+        dxp, lddx = alloc_rows(N, H * Cc, torch.float32, dev)
+        da_s = torch.empty((N, H), dtype=torch.float32, device=dev)
+        da_d = torch.zeros((N, H), dtype=torch.float32, device=dev)
+        tpos = g.tpos() if drop is not None else None
+        check(lib().rgbmp_gat_backward(g.bwd.ref, ptr(xb), xb.stride(0), ptr(a_s), ptr(a_d), H, Cc, ctx.slope,
+                                       ptr(drop), ptr(tpos), ptr(rmax), ptr(rsum), ptr(S), ptr(db), ldd, ptr(dxp),
+                                       lddx, ptr(da_s), ptr(da_d), dev.index, stream_of(dev)), "gat_backward")
+        return dxp, da_s, da_d, None, None, None, None, None
+
+
+def gat(xp, a_src, a_dst, graph: Graph, H: int, Cc: int, slope: float = 0.2, drop_edge: Optional[torch.Tensor] = None):
+    """xp [N,H*C], a_src/a_dst [N,H] -> [N,H*C].  drop_edge: optional [nnz,H] keep-mask/(1-p) in EDGE order."""
+    if gat_fusable(H, Cc):
+        drop_csr = graph.to_csr_order(drop_edge) if drop_edge is not None else None
+        return _GAT.apply(xp, a_src, a_dst, graph, H, Cc, float(slope), drop_csr)
+    e = torch.nn.functional.leaky_relu(edge_u_add_v(a_src, a_dst, graph), slope)
+    alpha = edge_softmax(e, graph)
+    if drop_edge is not None:
+        alpha = alpha * graph.to_csr_order(drop_edge)
+    return spmm_heads(alpha, xp, graph, H, Cc)
+
+
+class _EidView:
+    """The forward CSR re-read with col = eid: row i then lists the EDGE ids of its in-edges, so an
+    SpMM over a per-edge message matrix [nnz, F] is the segmented reduction of scatter(msg, dst)."""
+
+    def __init__(self, csr: CSR):
+        from ._lib import GraphStruct
+        self.n_rows, self.n_cols, self.nnz, self.device = csr.n_rows, csr.nnz, csr.nnz, csr.device
+        self._csr = csr
+        self.struct = GraphStruct(csr.n_rows, csr.nnz, csr.nnz, ptr(csr.rowptr), ptr(csr.eid), csr.chunk,
+                                  csr.long_chunk, csr.n_long, csr.n_items, ptr(csr.long_rows),
+                                  ptr(csr.long_item_ptr), ptr(csr.item_long), ptr(csr.item_start))
+        self.ref = C.byref(self.struct)
+
+    def spmm_workspace(self, F):
+        return self._csr.spmm_workspace(F)
+
+    def norm(self, mode):
+        return self._csr.norm(mode)
+
+
+class _SegmentReduce(torch.autograd.Function):
+    """out[i] = sum (or mean) of msg[e] over edges e with dst[e] == i  -- the aggregate step of a
+    MessagePassing layer whose user-defined `message` produced msg in edge order (A6)."""
+
+    @staticmethod
+    def forward(ctx, msg, graph: Graph, mean: bool):
+        view = graph._vals.get("eid_view")
+        if view is None:
+            view = _EidView(graph.fwd)
+            graph._vals["eid_view"] = view
+        ctx.graph, ctx.mean = graph, mean
+        if mean:
+            cnt = graph.fwd.norm(NORM_COUNT)
+            return spmm_raw(view, msg, ep=make_epilogue(row_scale=cnt, row_div=True), keep=(cnt,))
+        return spmm_raw(view, msg)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.graph
+        if ctx.mean:
+            dy = row_scale(dy, g.fwd.norm(NORM_COUNT), divide=True)
+        return dy.index_select(0, g.e_dst.long()), None, None
+
+
+def segment_reduce(msg: torch.Tensor, graph: Graph, mean: bool = False) -> torch.Tensor:
+    return _SegmentReduce.apply(msg, graph, bool(mean))
+
+
+class HostAppnpPlan:
+    """Device scratch for the host-buffer entry point, allocated once and reused across calls."""
+
+    def __init__(self, graph: Graph, F: int):
+        N, dev = graph.N, graph.device
+        self.graph, self.F, self.ld = graph, F, padded_width(F)
+        self.bufs = [torch.empty((N, self.ld), dtype=torch.float32, device=dev) for _ in range(4)]
+        self.ws = graph.fwd.spmm_workspace(F)
+        self.dinv = graph.dinv()
+
+
+def appnp_host(graph: Graph, z0_host: torch.Tensor, out_host: torch.Tensor, K: int, alpha: float,
+               plan: Optional[HostAppnpPlan] = None) -> torch.Tensor:
+    """End-to-end APPNP propagation with HOST buffers (pinned for full PCIe speed): one C-ABI call
+    does H2D, the D^-1/2 pre-scale, K fused hops and D2H, and returns when `out_host` is valid."""
+    if z0_host.is_cuda or out_host.is_cuda:
+        raise RuntimeError("appnp_host takes host tensors")
+    if z0_host.dtype != torch.float32 or not z0_host.is_contiguous() or not out_host.is_contiguous():
+        raise RuntimeError("appnp_host needs contiguous float32 host tensors")
+    N, F = z0_host.shape
+    if plan is None:
+        plan = HostAppnpPlan(graph, F)
+    dev = graph.device
+    z0d, ping, pong, outd = plan.bufs
+    check(lib().rgbmp_appnp_host(graph.fwd.ref, ptr(plan.dinv), z0_host.data_ptr(), out_host.data_ptr(), F, K,
+                                 float(alpha), ptr(z0d), ptr(ping), ptr(pong), ptr(outd), plan.ld, ptr(plan.ws),
+                                 0 if plan.ws is None else plan.ws.numel(), dev.index, stream_of(dev)), "appnp_host")
+    return out_host

@@ -1,0 +1,141 @@
+"""1-D node-row partition of the propagation across the GPUs of one NVSwitch box.
+
+Rank p owns the output rows [p*R, (p+1)*R) with R = ceil(N / P), the CSR rows of that block (global
+column ids) and the matching rows of every feature matrix.  One exchange step per hop: an
+all-gather of the iterate's rows (NCCL over NVLink 5 through ``torch.distributed``), after which
+each rank runs the SAME fused SpMM kernel on its row block.  The host logic (row ranges, edge
+bucketing, the exchange) is plain torch and runs under gloo on CPU for the world_size-2 tests;
+only ``build_local_csr`` / ``PartitionedAPPNP`` touch the CUDA library.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rows_per_rank(N: int, world: int) -> int:
+    return (N + world - 1) // world
+
+
+def row_range(N: int, rank: int, world: int) -> Tuple[int, int]:
+    R = rows_per_rank(N, world)
+    lo = min(N, rank * R)
+    return lo, min(N, lo + R)
+
+
+def local_edges(e_src: torch.Tensor, e_dst: torch.Tensor, lo: int, hi: int):
+    """Edges whose TARGET falls in [lo, hi), order preserved: (local target id, global source id).
+    Because the filter keeps the relative order, the stable CSR of the bucket equals the matching
+    row block of the global stable CSR."""
+    m = (e_dst >= lo) & (e_dst < hi)
+    return (e_dst[m] - lo).to(torch.int32), e_src[m].to(torch.int32)
+
+
+def all_gather_rows(local: torch.Tensor, full: torch.Tensor, group=None):
+    """full[p*R:(p+1)*R] = rank p's `local` ([R, ld], same shape on every rank)."""
+    dist.all_gather_into_tensor(full, local, group=group)
+    return full
+
+
+class PartitionedPropagator:
+    """Device-agnostic K-hop driver: z <- a * A_hat z + b * z0 on a row partition.
+
+    spmm(x_full [P*R, ld], z0_local, a, b) -> next local iterate [R, ld] is injected: the CUDA
+    kernel in production, the CPU oracle in the gloo tests."""
+
+    def __init__(self, N: int, rank: int, world: int, spmm: Callable, group=None):
+        self.N, self.rank, self.world, self.group = N, rank, world, group
+        self.R = rows_per_rank(N, world)
+        self.lo, self.hi = row_range(N, rank, world)
+        self.spmm = spmm
+
+    def run(self, z0_local: torch.Tensor, K: int, a: float, b: float,
+            full: Optional[torch.Tensor] = None) -> torch.Tensor:
+        R, ld = z0_local.shape
+        assert R == self.R, "every rank passes ceil(N/P) rows (pad the last block)"
+        if full is None:
+            full = torch.empty((R * self.world, ld), dtype=z0_local.dtype, device=z0_local.device)
+        cur = z0_local
+        for _ in range(K):
+            if self.world > 1:
+                all_gather_rows(cur, full, self.group)
+                src = full
+            else:
+                src = cur
+            cur = self.spmm(src, z0_local, a, b)
+        return cur
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA side
+# ------------------------------------------------------------------------------------------------
+class LocalBlock:
+    """This rank's CSR row block + normalisation, built by the integer kernels."""
+
+    def __init__(self, edge_index: torch.Tensor, N: int, loop_mode: int, rank: int, world: int, group=None):
+        from . import _lib
+        from ._lib import check, lib, ptr, stream_of
+        from .graph import CSR, NORM_INV_SQRT, _ws
+        L = lib()
+        dev = edge_index.device
+        E = edge_index.size(1)
+        ei = edge_index.contiguous()
+        e_src = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+        e_dst = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+        nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+        ws = _ws(L.rgbmp_edge_edit_workspace_bytes(E, N), dev)
+        check(L.rgbmp_edge_edit(ptr(ei[0]), ptr(ei[1]), E, N, loop_mode, ptr(e_src), ptr(e_dst), ptr(nnz_dev),
+                                ptr(ws), ws.numel(), dev.index, stream_of(dev)), "edge_edit")
+        nnz = int(nnz_dev.item())
+        if nnz < 0:
+            raise RuntimeError("edge_index contains node ids outside [0, N)")
+        self.nnz_global = nnz
+        self.N, self.rank, self.world = N, rank, world
+        self.R = rows_per_rank(N, world)
+        self.lo, self.hi = row_range(N, rank, world)
+        key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
+        del e_src, e_dst
+        self.csr = CSR(key, other, self.R, self.R * world)
+        self.nnz_local = key.numel()
+        self.dinv_local = self.csr.norm(NORM_INV_SQRT)                      # in-degrees of my rows are complete
+        self.dinv_full = torch.empty(self.R * world, dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.all_gather_into_tensor(self.dinv_full, self.dinv_local, group=group)
+        else:
+            self.dinv_full.copy_(self.dinv_local)
+        self.val = torch.empty(max(self.nnz_local, 1), dtype=torch.float32, device=dev)
+        check(L.rgbmp_gcn_edge_weight(ptr(self.csr.rowptr), ptr(self.csr.col), self.R, ptr(self.dinv_local),
+                                      ptr(self.dinv_full), ptr(self.val), dev.index, stream_of(dev)),
+              "gcn_edge_weight")
+
+
+class PartitionedAPPNP:
+    """APPNP / LP-style K-hop propagation over a LocalBlock; per hop: NCCL all-gather of the
+    iterate rows, then the fused SpMM (+teleport epilogue) on the local rows."""
+
+    def __init__(self, block: LocalBlock, F: int, group=None):
+        from . import ops
+        self.block, self.F, self.group = block, F, group
+        self.ld = ops.padded_width(F)
+        dev = block.csr.device
+        R, P = block.R, block.world
+        self.full = torch.empty((R * P, self.ld), dtype=torch.float32, device=dev)
+        self.ping = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
+        self.pong = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
+        self._flip = False
+
+        def spmm(x_full, z0_local, a, b):
+            out = self.pong if self._flip else self.ping
+            self._flip = not self._flip
+            ep = ops.make_epilogue(a=a, b=b, T=z0_local, ldt=z0_local.stride(0))
+            ops.spmm_raw(block.csr, x_full[:, :F], block.val, ep=ep, keep=(z0_local,), out=out[:, :F])
+            return out
+
+        self.driver = PartitionedPropagator(block.N, block.rank, block.world, spmm, group)
+        self.launches_per_hop = 1 + (2 if block.csr.n_items > 0 else 0)
+
+    def run(self, z0_local: torch.Tensor, K: int, alpha: float) -> torch.Tensor:
+        """z0_local: [R, ld] (padded rows beyond N are zero).  Returns this rank's rows of z_K."""
+        return self.driver.run(z0_local, K, 1.0 - alpha, alpha, self.full)

@@ -1,0 +1,185 @@
+"""torch_geometric.utils / torch_scatter / torch_sparse functions the reference imports
+(graphsage.py:4, dagnn.py:7,10, itexperiments.py:22, rd2pd.py:12).
+
+The self-loop edits run on the CUDA edge-edit kernel and are memoised on the identity of the
+input tensor, so ``my_SAGEConv.forward`` (graphsage.py:55-56), which re-derives its edge list on
+every call, gets the SAME result tensors back each epoch and the CSR cache behind ``propagate``
+keeps hitting."""
+from __future__ import annotations
+
+import threading
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from ..graph import (LOOP_ADD, LOOP_ADD_REMAINING, LOOP_NONE, LOOP_REMOVE_THEN_ADD, _ws)
+from .._lib import check, lib, ptr, stream_of
+
+_MEMO: "OrderedDict[tuple, tuple]" = OrderedDict()
+_MEMO_LOCK = threading.Lock()
+_MEMO_MAX = 32
+
+
+def _num_nodes(edge_index, num_nodes):
+    if num_nodes is not None:
+        return int(num_nodes)
+    return int(edge_index.max()) + 1 if edge_index.numel() else 0
+
+
+def _edit(edge_index: torch.Tensor, N: int, mode: int, filter_only: bool = False) -> torch.Tensor:
+    """Edited edge list as int64 [2, nnz] (memoised).  filter_only: drop loops, append none."""
+    _lib.require_cuda(edge_index, "edge_index")
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), N, mode, filter_only)
+    with _MEMO_LOCK:
+        hit = _MEMO.get(key)
+        if hit is not None:
+            _MEMO.move_to_end(key)
+            return hit[0]
+    L = lib()
+    dev = edge_index.device
+    ei = edge_index.contiguous()
+    E = ei.size(1)
+    e_src = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+    e_dst = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+    nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = _ws(L.rgbmp_edge_edit_workspace_bytes(E, N), dev)
+    check(L.rgbmp_edge_edit(ptr(ei[0]) if E else None, ptr(ei[1]) if E else None, E, N, mode, ptr(e_src), ptr(e_dst),
+                            ptr(nnz_dev), ptr(ws), ws.numel(), dev.index, stream_of(dev)), "edge_edit")
+    nnz = int(nnz_dev.item())
+    if nnz < 0:
+        raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
+    if filter_only:
+        nnz -= N
+    out = torch.stack([e_src[:nnz], e_dst[:nnz]]).to(torch.int64)
+    with _MEMO_LOCK:
+        _MEMO[key] = (out, edge_index)
+        while len(_MEMO) > _MEMO_MAX:
+            _MEMO.popitem(last=False)
+    return out
+
+
+def remove_self_loops(edge_index, edge_attr=None):
+    """A1 (graphsage.py:55)."""
+    if edge_attr is not None:
+        mask = edge_index[0] != edge_index[1]
+        return edge_index[:, mask], edge_attr[mask]
+    N = _num_nodes(edge_index, None)
+    return _edit(edge_index, N, LOOP_REMOVE_THEN_ADD, filter_only=True), None
+
+
+def add_self_loops(edge_index, edge_weight=None, fill_value=1.0, num_nodes=None):
+    """A2 (graphsage.py:56)."""
+    N = _num_nodes(edge_index, num_nodes)
+    out = _edit(edge_index, N, LOOP_ADD)
+    if edge_weight is not None:
+        edge_weight = torch.cat([edge_weight, edge_weight.new_full((N,), fill_value)])
+    return out, edge_weight
+
+
+def add_remaining_self_loops(edge_index, edge_weight=None, fill_value=1.0, num_nodes=None):
+    """A3 (dagnn.py:22-23)."""
+    N = _num_nodes(edge_index, num_nodes)
+    out = _edit(edge_index, N, LOOP_ADD_REMAINING)
+    if edge_weight is not None:
+        row, col = edge_index[0], edge_index[1]
+        mask = row != col
+        lw = edge_weight.new_full((N,), fill_value)
+        inv = ~mask
+        rem = edge_weight[inv]
+        if rem.numel() > 0:
+            lw[row[inv]] = rem
+        edge_weight = torch.cat([edge_weight[mask], lw])
+    return out, edge_weight
+
+
+def _bcast(index, src, dim):
+    if dim < 0:
+        dim = src.dim() + dim
+    if index.dim() == 1:
+        for _ in range(dim):
+            index = index.unsqueeze(0)
+    for _ in range(index.dim(), src.dim()):
+        index = index.unsqueeze(-1)
+    return index.expand_as(src)
+
+
+def scatter_add(src, index, dim=-1, out=None, dim_size=None):
+    """torch_scatter.scatter_add (dagnn.py:28: the degree vector of gcn_norm).  Node-sized helper
+    outside the aggregation hot loop; stays a device-side torch scatter (host glue)."""
+    index = _bcast(index, src, dim)
+    if out is None:
+        size = list(src.size())
+        size[dim] = dim_size if dim_size is not None else (int(index.max()) + 1 if index.numel() else 0)
+        out = torch.zeros(size, dtype=src.dtype, device=src.device)
+    return out.scatter_add_(dim, index, src)
+
+
+def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
+    if reduce in ("sum", "add"):
+        return scatter_add(src, index, dim, None, dim_size)
+    if reduce == "mean":
+        out = scatter_add(src, index, dim, None, dim_size)
+        n = out.size(dim)
+        cnt = scatter_add(torch.ones(index.size(0), dtype=src.dtype, device=src.device), index, 0, None, n)
+        cnt[cnt < 1] = 1
+        shape = [1] * out.dim()
+        shape[dim] = n
+        return out / cnt.view(shape)
+    if reduce == "max":
+        size = list(src.size())
+        size[dim] = dim_size if dim_size is not None else int(index.max()) + 1
+        out = torch.zeros(size, dtype=src.dtype, device=src.device)
+        return out.scatter_reduce_(dim, _bcast(index, src, dim), src, reduce="amax", include_self=False)
+    raise ValueError(reduce)
+
+
+def coalesce(index, value, m, n, op="add"):
+    """torch_sparse.coalesce (rd2pd.py:93): sort by row*n+col, unique.  ("next" row f1)"""
+    key = index[0] * n + index[1]
+    uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+    out_index = torch.stack([uniq // n, uniq % n])
+    if value is None:
+        return out_index, None
+    return out_index, scatter(value, inv, 0, uniq.numel(), "sum" if op == "add" else op)
+
+
+def to_undirected(edge_index, num_nodes=None):
+    """A16 (itexperiments.py:238).  ("next" row f1)"""
+    N = _num_nodes(edge_index, num_nodes)
+    row, col = edge_index[0], edge_index[1]
+    row, col = torch.cat([row, col]), torch.cat([col, row])
+    return coalesce(torch.stack([row, col]), None, N, N)[0]
+
+
+def dropout_adj(edge_index, p=0.5, training=True):
+    if not training or p == 0.0:
+        return edge_index, None
+    mask = torch.full((edge_index.size(1),), 1 - p, dtype=torch.float, device=edge_index.device)
+    mask = torch.bernoulli(mask).to(torch.bool)
+    return edge_index[:, mask], None
+
+
+def negative_sampling(edge_index, num_nodes, num_neg_samples):
+    N = num_nodes
+    idx = edge_index[0] * N + edge_index[1]
+    size = N * N
+    num_neg = min(int(num_neg_samples), size - idx.numel())
+    if num_neg <= 0:
+        return edge_index.new_empty((2, 0))
+    alpha = abs(1 / (1 - 1.1 * (edge_index.size(1) / size)))
+    sample_size = int(alpha * num_neg)
+    neg = None
+    for _ in range(3):
+        rnd = torch.randint(size, (sample_size,), dtype=torch.long, device=edge_index.device)
+        rnd = rnd[~torch.isin(rnd, idx)]
+        neg = rnd if neg is None else torch.cat([neg, rnd])
+        if neg.numel() >= num_neg:
+            neg = neg[:num_neg]
+            break
+    return torch.stack([neg // N, neg % N])
+
+
+def to_networkx(data, *args, **kwargs):               # imported at dagnn.py:7, never called
+    raise NotImplementedError("to_networkx is imported by the reference but never used")

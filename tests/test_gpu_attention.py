@@ -1,0 +1,269 @@
+"""Attention kernels: fused GAT forward/backward, SDDMM, edge softmax, multi-head weighted SpMM,
+and the SuperGAT / FAConv layers built from them, against the oracle (fp64 arbiter).  Through the C ABI."""
+import pytest
+import torch
+
+from helpers import CASES, relerr
+from oracle import layers as OL
+from oracle import pyg_restated as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def P():
+    import rgb_experiment_b200 as P_
+    return P_
+
+
+@pytest.mark.parametrize("case", ["tiny", "loops_dups", "isolated", "hub", "medium"])
+@pytest.mark.parametrize("H,C", [(8, 8), (1, 41), (1, 7), (2, 16), (4, 4), (3, 5), (1, 130)])
+def test_gat_forward_backward(case, H, C):
+    p = P()
+    ei, n = CASES[case]()
+    gen = torch.Generator().manual_seed(H * 1000 + C)
+    xp = torch.randn(n, H, C, generator=gen)
+    a_s = torch.randn(n, H, generator=gen)
+    a_d = torch.randn(n, H, generator=gen)
+    dout = torch.randn(n, H * C, generator=gen)
+    xo, so, do_ = (t.double().requires_grad_(True) for t in (xp, a_s, a_d))
+    out_o, _, _ = R.gat_aggregate(xo, so, do_, ei, 0.2)
+    out_o.reshape(n, H * C).backward(dout.double())
+    g = p.Graph(ei.to(DEV), n, p.LOOP_REMOVE_THEN_ADD)
+    xg = xp.view(n, H * C).to(DEV).requires_grad_(True)
+    sg, dg = a_s.to(DEV).requires_grad_(True), a_d.to(DEV).requires_grad_(True)
+    out = p.ops.gat(xg, sg, dg, g, H, C, 0.2)
+    out.backward(dout.to(DEV))
+    assert relerr(out.detach(), out_o.detach().reshape(n, H * C)) <= TOL
+    assert relerr(xg.grad, xo.grad.reshape(n, H * C)) <= TOL
+    assert relerr(sg.grad, so.grad) <= 2e-5          # da_dst / da_src: cancellation of alpha*(dalpha - S)
+    assert relerr(dg.grad, do_.grad) <= 2e-5
+
+
+def test_gat_softmax_rows_sum_to_one_at_reddit_like_degree():
+    """Size-independent property on a dense-ish graph: with Xp = 1, out = sum_j alpha_ij = 1."""
+    p = P()
+    import rgb_experiment_b200.synth as S
+    sg = S.make_graph(20_000, 4_000_000, 8, 4, features=False, device=DEV)
+    n, H, C = sg.num_nodes, 8, 8
+    g = p.Graph(sg.edge_index, n, p.LOOP_REMOVE_THEN_ADD)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    a_s = torch.randn(n, H, device=DEV, generator=gen) * 3
+    a_d = torch.randn(n, H, device=DEV, generator=gen) * 3
+    out = p.ops.gat(torch.ones(n, H * C, device=DEV), a_s, a_d, g, H, C, 0.2)
+    assert (out - 1).abs().max().item() <= 1e-5
+
+
+def test_gat_attention_dropout_mask_in_edge_order():
+    p = P()
+    ei, n = CASES["loops_dups"]()
+    H, C = 4, 8
+    gen = torch.Generator().manual_seed(1)
+    xp = torch.randn(n, H, C, generator=gen)
+    a_s, a_d = torch.randn(n, H, generator=gen), torch.randn(n, H, generator=gen)
+    ed = R.edit_loops(ei, n, R.LOOP_REMOVE_THEN_ADD)
+    keep = (torch.rand(ed.size(1), H, generator=gen) > 0.3).float() / 0.7
+    dout = torch.randn(n, H * C, generator=gen)
+    xo, so, do_ = (t.double().requires_grad_(True) for t in (xp, a_s, a_d))
+    out_o, _, _ = R.gat_aggregate(xo, so, do_, ei, 0.2, alpha_dropout_mask=keep.double())
+    out_o.reshape(n, -1).backward(dout.double())
+    g = p.Graph(ei.to(DEV), n, p.LOOP_REMOVE_THEN_ADD)
+    xg = xp.view(n, -1).to(DEV).requires_grad_(True)
+    sg, dg = a_s.to(DEV).requires_grad_(True), a_d.to(DEV).requires_grad_(True)
+    out = p.ops.gat(xg, sg, dg, g, H, C, 0.2, keep.to(DEV))
+    out.backward(dout.to(DEV))
+    assert relerr(out.detach(), out_o.detach().reshape(n, -1)) <= TOL
+    assert relerr(xg.grad, xo.grad.reshape(n, -1)) <= TOL
+    assert relerr(sg.grad, so.grad) <= 2e-5 and relerr(dg.grad, do_.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("case", ["loops_dups", "hub"])
+def test_edge_score_kernels(case):
+    p = P()
+    ei, n = CASES[case]()
+    H, C = 3, 6
+    gen = torch.Generator().manual_seed(2)
+    A = torch.randn(n, H * C, generator=gen)
+    B = torch.randn(n, H * C, generator=gen)
+    u, v = torch.randn(n, H, generator=gen), torch.randn(n, H, generator=gen)
+    g = p.Graph(ei.to(DEV), n, p.LOOP_NONE)
+    row, col = ei[0], ei[1]
+    # SDDMM  (edge order after un-permuting)
+    Ao, Bo = A.double().requires_grad_(True), B.double().requires_grad_(True)
+    so = (Ao.view(n, H, C)[col] * Bo.view(n, H, C)[row]).sum(-1)
+    ge = torch.randn(ei.size(1), H, generator=gen)
+    so.backward(ge.double())
+    Ag, Bg = A.to(DEV).requires_grad_(True), B.to(DEV).requires_grad_(True)
+    sg = p.ops.edge_sddmm(Ag, Bg, g, H, C)
+    sg.backward(g.to_csr_order(ge.to(DEV)))
+    assert relerr(g.to_edge_order(sg.detach()), so.detach()) <= TOL
+    assert relerr(Ag.grad, Ao.grad) <= TOL and relerr(Bg.grad, Bo.grad) <= TOL
+    # u_add_v
+    uo, vo = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    eo = uo[row] + vo[col]
+    eo.backward(ge.double())
+    ug, vg = u.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    eg = p.ops.edge_u_add_v(ug, vg, g)
+    eg.backward(g.to_csr_order(ge.to(DEV)))
+    assert relerr(g.to_edge_order(eg.detach()), eo.detach()) <= TOL
+    assert relerr(ug.grad, uo.grad) <= TOL and relerr(vg.grad, vo.grad) <= TOL
+    # edge softmax
+    lo = ge.double().requires_grad_(True)
+    ao = R.softmax(lo, col, num_nodes=n)
+    g2 = torch.randn(ei.size(1), H, generator=gen)
+    ao.backward(g2.double())
+    lg = g.to_csr_order(ge.to(DEV)).requires_grad_(True)
+    ag = p.ops.edge_softmax(lg, g)
+    ag.backward(g.to_csr_order(g2.to(DEV)))
+    assert relerr(g.to_edge_order(ag.detach()), ao.detach()) <= TOL
+    assert relerr(g.to_edge_order(lg.grad), lo.grad) <= TOL
+    # weighted multi-head SpMM
+    wo = g2.double().requires_grad_(True)
+    Xo = A.double().requires_grad_(True)
+    oo = R.scatter_add(Xo.view(n, H, C)[row] * wo.unsqueeze(-1), col, 0, dim_size=n).reshape(n, -1)
+    dout = torch.randn(n, H * C, generator=gen)
+    oo.backward(dout.double())
+    wg = g.to_csr_order(g2.to(DEV)).requires_grad_(True)
+    Xg = A.to(DEV).requires_grad_(True)
+    og = p.ops.spmm_heads(wg, Xg, g, H, C)
+    og.backward(dout.to(DEV))
+    assert relerr(og.detach(), oo.detach()) <= TOL
+    assert relerr(Xg.grad, Xo.grad) <= TOL
+    assert relerr(g.to_edge_order(wg.grad), wo.grad) <= TOL
+
+
+def _pair(name, args, kw, seed=0):
+    import importlib
+    PL = importlib.import_module("rgb_experiment_b200.shim.nn")
+    torch.manual_seed(seed)
+    o = getattr(OL, name)(*args, **kw).double()
+    torch.manual_seed(seed)
+    g = getattr(PL, name)(*args, **kw)
+    g.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+    return o.eval(), g.to(DEV).eval()
+
+
+def _check_layer(o, g, inputs_cpu, ei, tol=TOL):
+    xs_o = [t.double().requires_grad_(True) for t in inputs_cpu]
+    xs_g = [t.to(DEV).requires_grad_(True) for t in inputs_cpu]
+    yo = o(*xs_o, ei)
+    yg = g(*xs_g, ei.to(DEV))
+    assert relerr(yg.detach(), yo.detach()) <= tol
+    dy = torch.randn(yo.shape, generator=torch.Generator().manual_seed(9))
+    yo.backward(dy.double())
+    yg.backward(dy.to(DEV))
+    for a, b in zip(xs_g, xs_o):
+        assert relerr(a.grad, b.grad) <= 2 * tol
+    po, pg = dict(o.named_parameters()), dict(g.named_parameters())
+    for k in po:
+        if po[k].grad is not None:
+            assert relerr(pg[k].grad, po[k].grad) <= 3 * tol, k
+
+
+@pytest.mark.parametrize("case", ["loops_dups", "hub"])
+def test_supergat_layer_eval_mode(case):
+    ei, n = CASES[case]()
+    x = torch.randn(n, 12, generator=torch.Generator().manual_seed(3))
+    o, g = _pair("SuperGATConv", (12, 4), {"heads": 3, "dropout": 0.5})
+    _check_layer(o, g, [x], ei)
+    o, g = _pair("SuperGATConv", (12, 5), {"heads": 2, "concat": False})
+    _check_layer(o, g, [x], ei)
+    assert float(g.get_attention_loss()) == 0.0
+
+
+def test_supergat_training_mode_loss_is_finite_and_differentiable():
+    ei, n = CASES["loops_dups"]()
+    x = torch.randn(n, 12, generator=torch.Generator().manual_seed(3)).to(DEV)
+    _, g = _pair("SuperGATConv", (12, 4), {"heads": 2, "dropout": 0.2, "edge_sample_ratio": 0.8,
+                                           "neg_sample_ratio": 0.5})
+    g.train()
+    out = g(x, ei.to(DEV))
+    loss = out.sum() + 4.0 * g.get_attention_loss()
+    loss.backward()
+    assert torch.isfinite(loss) and all(torch.isfinite(p_.grad).all() for p_ in g.parameters())
+
+
+@pytest.mark.parametrize("case", ["loops_dups", "hub"])
+def test_faconv_layer(case):
+    ei, n = CASES[case]()
+    gen = torch.Generator().manual_seed(4)
+    x, x0 = torch.randn(n, 16, generator=gen), torch.randn(n, 16, generator=gen)
+    o, g = _pair("FAConv", (16, 0.3, 0.5), {})
+    _check_layer(o, g, [x, x0], ei)
+
+
+@pytest.mark.parametrize("name,args,kw,F", [
+    ("GCNConv", (20, 7), {}, 20), ("SAGEConv", (20, 7), {}, 20), ("GATConv", (20, 8), {"heads": 8}, 20),
+    ("GATConv", (20, 7), {"heads": 1, "concat": False}, 20), ("SGConv", (20, 7), {"K": 2}, 20),
+    ("APPNP", (10, 0.1), {}, 7), ("GatedGraphConv", (24, 2), {}, 20),
+])
+@pytest.mark.parametrize("case", ["loops_dups", "hub"])
+def test_conv_layers_match_oracle_layers(name, args, kw, F, case):
+    ei, n = CASES[case]()
+    x = torch.randn(n, F, generator=torch.Generator().manual_seed(5))
+    o, g = _pair(name, args, kw)
+    _check_layer(o, g, [x], ei, tol=2e-5 if name == "GatedGraphConv" else TOL)
+
+
+def test_ginconv_layer():
+    import importlib
+    PL = importlib.import_module("rgb_experiment_b200.shim.nn")
+    ei, n = CASES["loops_dups"]()
+    x = torch.randn(n, 10, generator=torch.Generator().manual_seed(6))
+    torch.manual_seed(0)
+    mo = torch.nn.Sequential(torch.nn.Linear(10, 8), torch.nn.ReLU(), torch.nn.Linear(8, 8))
+    o = OL.GINConv(mo, train_eps=True).double()
+    torch.manual_seed(0)
+    mg = torch.nn.Sequential(torch.nn.Linear(10, 8), torch.nn.ReLU(), torch.nn.Linear(8, 8))
+    g = PL.GINConv(mg, train_eps=True)
+    g.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+    _check_layer(o, g.to(DEV), [x], ei)
+
+
+def test_user_defined_message_passing_subclasses():
+    """The two in-tree MessagePassing subclasses of the reference, restated: mean of x_j
+    (graphsage.py:36-62) and add of norm*x_j (dagnn.py:34-65), plus an arbitrary message."""
+    import importlib
+    PL = importlib.import_module("rgb_experiment_b200.shim.nn")
+    ei, n = CASES["loops_dups"]()
+    x = torch.randn(n, 6, generator=torch.Generator().manual_seed(7))
+    w = torch.rand(ei.size(1), generator=torch.Generator().manual_seed(8))
+
+    def make(base):
+        class Mean(base):
+            def __init__(self):
+                super().__init__(aggr="mean")
+
+            def forward(self, x, ei):
+                return self.propagate(ei, x=x)
+
+        class Weighted(base):
+            def __init__(self):
+                super().__init__(aggr="add")
+
+            def forward(self, x, ei, norm):
+                return self.propagate(ei, x=x, norm=norm)
+
+            def message(self, x_j, norm):
+                return norm.view(-1, 1) * x_j
+
+        class Odd(base):
+            def __init__(self):
+                super().__init__(aggr="add")
+
+            def forward(self, x, ei):
+                return self.propagate(ei, x=x)
+
+            def message(self, x_i, x_j):
+                return torch.tanh(x_i) * x_j
+
+        return Mean(), Weighted(), Odd()
+
+    mo, wo, oo = make(OL.MessagePassing)
+    mg, wg, og = make(PL.MessagePassing)
+    d = ei.to(DEV)
+    assert relerr(mg(x.to(DEV), d), mo(x, ei)) <= TOL
+    assert relerr(wg(x.to(DEV), d, w.to(DEV)), wo(x, ei, w)) <= TOL
+    assert relerr(og(x.to(DEV), d), oo(x, ei)) <= TOL
+    assert PL._is_weighted_message(type(wg), "norm") and not PL._is_weighted_message(type(og), "x_j")

@@ -1,0 +1,120 @@
+"""Integer graph-build kernels vs the oracle -- BIT-EXACT.  Through the C ABI."""
+import pytest
+import torch
+
+from helpers import CASES, GOLDEN, load_golden
+from oracle import pyg_restated as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def product():
+    import rgb_experiment_b200 as P
+    return P
+
+
+def check_graph(ei, n, mode):
+    P = product()
+    g = P.Graph(ei.to(DEV), n, mode)
+    ed = R.edit_loops(ei, n, mode)
+    assert g.nnz == ed.size(1)
+    assert torch.equal(g.e_src.cpu().long(), ed[0]) and torch.equal(g.e_dst.cpu().long(), ed[1])
+    for csr, by in ((g.fwd, "dst"), (g.bwd, "src")):
+        rowptr, col, eid = R.csr_build(ed, n, by)
+        assert csr.rowptr.dtype == torch.int64 and csr.col.dtype == torch.int32
+        assert torch.equal(csr.rowptr.cpu(), rowptr)
+        assert torch.equal(csr.col.cpu().long(), col)
+        assert torch.equal(csr.eid.cpu().long(), eid)
+    deg = R.degree(ed, n, "dst")
+    assert torch.equal(g.fwd.degree().cpu(), deg)
+    dinv = deg.float().pow(-0.5)
+    dinv[dinv == float("inf")] = 0
+    assert torch.equal(g.dinv().cpu(), dinv)
+    return g, ed
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_edit_and_csr_bit_exact(case, mode):
+    ei, n = CASES[case]()
+    check_graph(ei, n, mode)
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_gcn_norm_weights_match_reference_golden(path):
+    """dagnn.py:12-31 executed verbatim in the build container (tests/golden)."""
+    P = product()
+    gold = load_golden(path)
+    ei, n = gold["edge_index"], gold["num_nodes"]
+    g = P.Graph(ei.to(DEV), n, P.LOOP_ADD_REMAINING)
+    assert torch.equal(g.edge_index().cpu(), gold["gcn_norm_edge_index"])
+    w_edge = g.to_edge_order(g.gcn_val(False)).cpu()
+    assert torch.equal(w_edge, gold["gcn_norm_weight"])                 # same multiplication order -> bitwise
+    g0 = P.Graph(ei.to(DEV), n, P.LOOP_NONE)
+    assert torch.equal(g0.to_edge_order(g0.gcn_val(False)).cpu(), gold["gcn_norm_noloop_weight"])
+    # transpose weights are the same numbers in transpose order
+    assert torch.equal(g.to_edge_order(g.gcn_val(True), transpose=True).cpu(), gold["gcn_norm_weight"])
+
+
+def test_arxiv_shaped_graph_bit_exact_and_long_rows():
+    P = product()
+    import rgb_experiment_b200.synth as S
+    sg = S.make_named("arxiv", features=False)
+    g, ed = check_graph(sg.edge_index, sg.num_nodes, P.LOOP_ADD_REMAINING)
+    csr = g.fwd
+    deg = csr.degree().cpu()
+    long_rows = torch.nonzero(deg > csr.chunk).flatten()
+    assert csr.n_long == long_rows.numel() and csr.n_long > 0
+    assert torch.equal(csr.long_rows.cpu().long(), long_rows)
+    items = (deg[long_rows] + csr.long_chunk - 1) // csr.long_chunk
+    assert csr.n_items == int(items.sum())
+    ptrs = csr.long_item_ptr.cpu().long()
+    assert torch.equal(ptrs[1:] - ptrs[:-1], items)
+    starts = csr.item_start.cpu()
+    il = csr.item_long.cpu().long()
+    for s in range(min(csr.n_long, 20)):
+        r = long_rows[s]
+        mine = starts[ptrs[s]:ptrs[s + 1]]
+        exp = csr.rowptr.cpu()[r] + torch.arange(items[s]) * csr.long_chunk
+        assert torch.equal(mine, exp) and torch.all(il[ptrs[s]:ptrs[s + 1]] == s)
+
+
+def test_out_of_range_node_id_raises():
+    P = product()
+    ei = torch.tensor([[0, 1, 9], [1, 2, 0]])
+    with pytest.raises(RuntimeError, match="outside"):
+        P.Graph(ei.to(DEV), 5, P.LOOP_NONE)
+    with pytest.raises(RuntimeError, match="outside"):
+        P.Graph(torch.tensor([[0, -1], [1, 0]]).to(DEV), 5, P.LOOP_ADD)
+
+
+def test_cache_hits_on_same_tensor_and_loop_utils_are_memoised():
+    P = product()
+    from rgb_experiment_b200.shim import utils as U
+    ei, n = CASES["loops_dups"]()
+    d = ei.to(DEV)
+    P.graph.clear_cache()
+    a = P.get_graph(d, n, P.LOOP_ADD_REMAINING)
+    b = P.get_graph(d, n, P.LOOP_ADD_REMAINING)
+    assert a is b
+    assert P.get_graph(d, n, P.LOOP_NONE) is not a
+    r1, _ = U.remove_self_loops(d)
+    r2, _ = U.add_self_loops(r1, num_nodes=n)
+    r1b, _ = U.remove_self_loops(d)
+    r2b, _ = U.add_self_loops(r1b, num_nodes=n)
+    assert r1 is r1b and r2 is r2b                       # graphsage.py:55-56 re-derives these every forward
+    assert torch.equal(r2.cpu(), R.edit_loops(ei, n, R.LOOP_REMOVE_THEN_ADD))
+    assert torch.equal(U.add_remaining_self_loops(d, num_nodes=n)[0].cpu(), R.edit_loops(ei, n, R.LOOP_ADD_REMAINING))
+    d2 = d.clone()
+    d2[0, 0] = (d2[0, 0] + 1) % n                        # in-place edit bumps _version -> new graph
+    v0 = P.get_graph(d2, n, P.LOOP_NONE)
+    d2[0, 0] = (d2[0, 0] + 1) % n
+    assert P.get_graph(d2, n, P.LOOP_NONE) is not v0
+
+
+def test_to_undirected_and_coalesce_match_oracle():
+    from rgb_experiment_b200.shim import utils as U
+    ei, n = CASES["loops_dups"]()
+    assert torch.equal(U.to_undirected(ei.to(DEV), n).cpu(), R.to_undirected(ei, n))
+    assert torch.equal(U.coalesce(ei.to(DEV), None, n, n)[0].cpu(), R.coalesce(ei, None, n, n)[0])

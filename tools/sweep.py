@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""On-GPU sweep of the SpMM launch shapes (G lanes per row, V vectors per lane, U edges in flight)
+for the BASELINE shapes.  Prints one JSON line per (workload, F, dtype, G, V, U) with the CUDA-event
+time per launch and the algorithmic GB/s, so that choose_shape() in csrc/spmm.cu can be set from
+measurements rather than guesses.   python tools/sweep.py [--workloads products,arxiv] [--quick]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def time_ms(fn, iters):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workloads", default="products,arxiv")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--chunks", default="")
+    args = ap.parse_args()
+    import rgb_experiment_b200 as P
+    import rgb_experiment_b200.synth as S
+    from rgb_experiment_b200 import graph as G_
+    dev = torch.device("cuda:0")
+    plans = {"products": [(47, torch.float32), (100, torch.float32)],
+             "arxiv": [(256, torch.float32), (40, torch.float32), (128, torch.bfloat16)],
+             "reddit": [(64, torch.float32), (41, torch.float32)]}
+    for wl in args.workloads.split(","):
+        sg = S.make_named(wl, device=dev, features=False)
+        N = sg.num_nodes
+        chunk_opts = [(1024, 4096)]
+        if args.chunks:
+            chunk_opts = [tuple(int(v) for v in c.split(":")) for c in args.chunks.split(",")]
+        for chunk, lchunk in chunk_opts:
+            g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING, chunk=chunk, long_chunk=lchunk)
+            val = g.gcn_val(False)
+            deg = g.fwd.degree()
+            print(json.dumps({"workload": wl, "N": N, "nnz": g.nnz, "max_deg": int(deg.max()), "n_long": g.fwd.n_long,
+                              "n_items": g.fwd.n_items, "chunk": chunk, "long_chunk": lchunk}), flush=True)
+            for F, dt in plans[wl]:
+                x = torch.randn(N, F, device=dev).to(dt)
+                xb, ld = P.ops.as_rows(x)
+                esz = 2 if dt == torch.bfloat16 else 4
+                nvec = (F * esz + 15) // 16
+                out, _ = P.ops.alloc_rows(N, F, dt, dev)
+                iters = 3 if args.quick else 5
+                for weighted in (True, False):
+                    res = []
+                    for G in (1, 2, 4, 8, 16, 32):
+                        for V in (1, 2, 3, 4):
+                            if G * V < nvec and nvec <= 128:
+                                continue
+                            if G * V >= 2 * nvec + 4:
+                                continue
+                            for U in (2, 4, 8):
+                                tune = G | (V << 8) | (U << 16)
+                                fn = lambda: P.ops.spmm_raw(g.fwd, xb, val if weighted else None, tune=tune, out=out)
+                                ms = time_ms(fn, iters)
+                                B = g.nnz * (F * esz + 4 + (4 if weighted else 0)) + N * F * esz + (N + 1) * 8
+                                r = {"workload": wl, "F": F, "dtype": str(dt).split(".")[-1], "weighted": weighted,
+                                     "G": G, "V": V, "U": U, "ms": round(ms, 4), "GBps": round(B / ms / 1e6, 1),
+                                     "gteps": round(g.nnz / ms / 1e6, 3), "chunk": chunk}
+                                res.append(r)
+                                print(json.dumps(r), flush=True)
+                    best = min(res, key=lambda r: r["ms"])
+                    default_ms = time_ms(lambda: P.ops.spmm_raw(g.fwd, xb, val if weighted else None, out=out), iters)
+                    print(json.dumps({"BEST": best, "default_ms": round(default_ms, 4)}), flush=True)
+            del g
+        del sg
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
