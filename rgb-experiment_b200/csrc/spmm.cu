@@ -3,24 +3,44 @@
 
 namespace rgbmp {
 
-// choose (G, V, U) for nvec vectors per row
+// packed [n,F] -> pitched z0 [n,ld] and u0 = scale*z0 [n,ld]  (host entry point staging)
+__global__ void __launch_bounds__(256)
+stage_rows_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, float* __restrict__ Z0,
+                  float* __restrict__ U0, int64_t ld, int64_t n_rows, int F) {
+  const int64_t total = n_rows * ld;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t r = t / ld;
+    const int f = (int)(t - r * ld);
+    const float v = (f < F) ? X[r * ldx + f] : 0.f;
+    Z0[t] = v;
+    U0[t] = __fmul_rn(scale[r], v);
+  }
+}
+
+// pitched [n,ld] -> packed [n,F]
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ X, int64_t ld, float* __restrict__ Y, int64_t n_rows, int F) {
+  const int64_t total = n_rows * F;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t r = t / F;
+    Y[t] = X[r * ld + (t - r * F)];
+  }
+}
+
+// choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 (tools/sweep.py,
+// profiles/sweep_r01.txt): the fastest shapes keep V*U ~ 4 independent 16-byte loads in flight per
+// lane and give a row as many lanes as it has vectors (V = 1) -- wider groups coalesce better and
+// put fewer rows of different length in one warp; U = 8 or V >= 3 always lost (L1tex queueing).
 static void choose_shape(int nvec, int* G, int* V, int* U) {
   if (nvec > 128) nvec = 128;  // wider rows are tiled over blockIdx.y
-  int bestG = 32, bestV = 4, bestWaste = 1 << 30;
-  const int Gs[6] = {32, 16, 8, 4, 2, 1};
-  for (int v = 1; v <= 4; ++v) {
-    for (int gi = 0; gi < 6; ++gi) {
-      const int g = Gs[gi];
-      if (g * v < nvec) continue;
-      const int waste = g * v - nvec;
-      // prefer no waste, then V<=2 (more rows per warp hurts less than idle lanes), then larger G
-      const int score = waste * 16 + (v > 2 ? 2 : 0) + (v == 1 ? 1 : 0);
-      if (score < bestWaste) { bestWaste = score; bestG = g; bestV = v; }
-    }
-  }
-  *G = bestG;
-  *V = bestV;
-  *U = 4;
+  int g = 1;
+  while (g < nvec && g < 32) g <<= 1;
+  int v = (nvec + g - 1) / g;
+  *G = g;
+  *V = v;
+  *U = (v <= 1) ? 4 : (v == 2 ? 4 : 2);
 }
 
 static int check_graph(const rgbmp_graph_t* g, const char* fn) {
@@ -199,11 +219,13 @@ int rgbmp_appnp_host(const rgbmp_graph_t* g, const float* dinv, const float* z0_
   if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_appnp_host: bad device");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = g->n_rows;
-  RGBMP_CUDA(cudaMemcpy2DAsync(dev_z0, ld * sizeof(float), z0_host, F * sizeof(float), F * sizeof(float), N,
-                               cudaMemcpyHostToDevice, st));
-  // u0 = D^-1/2 z0 (into pong, which hop 1 reads; hop 1 writes ping)
-  rc = rgbmp_row_scale(dev_z0, ld, dinv, 0, dev_pong, ld, N, F, RGBMP_F32, device, stream);
-  if (rc) return rc;
+  // One contiguous H2D at full PCIe rate into dev_out (used as the packed [N,F] staging area; a
+  // pitched 2-D copy of 188-byte rows runs ~15x slower), then one kernel re-pitches to ld and
+  // writes both z0 and u0 = D^-1/2 z0.
+  float* stage = dev_out;
+  RGBMP_CUDA(cudaMemcpyAsync(stage, z0_host, (size_t)N * F * sizeof(float), cudaMemcpyHostToDevice, st));
+  stage_rows_kernel<<<kSMs * 8, 256, 0, st>>>(stage, F, dinv, dev_z0, dev_pong, ld, N, F);
+  RGBMP_LAUNCH_CHECK("stage_rows_kernel");
   rgbmp_epilogue_t e = {};
   e.row_scale = dinv;
   e.a = 1.0f - alpha;
@@ -211,12 +233,15 @@ int rgbmp_appnp_host(const rgbmp_graph_t* g, const float* dinv, const float* z0_
   e.T = dev_z0;
   e.ldt = ld;
   e.out2_scale = dinv;
-  // hop k writes (k odd ? pong : ping); the first hop reads pong, so start the ping/pong at ping
+  // hop 1 reads u0 from pong and writes ping; the last hop writes the unscaled result to dev_out
   rc = rgbmp_khop(g, nullptr, dev_pong, ld, dev_ping, dev_pong, ld, dev_out, ld, nullptr, 0, 0, F, RGBMP_F32, K, &e, 0, ws,
                   ws_bytes, device, stream);
   if (rc) return rc;
-  RGBMP_CUDA(cudaMemcpy2DAsync(out_host, F * sizeof(float), dev_out, ld * sizeof(float), F * sizeof(float), N,
-                               cudaMemcpyDeviceToHost, st));
+  // pack [N, ld] -> [N, F] (ping is free once the last hop has run) and copy out contiguously
+  float* packed = dev_ping;
+  pack_rows_kernel<<<kSMs * 8, 256, 0, st>>>(dev_out, ld, packed, N, F);
+  RGBMP_LAUNCH_CHECK("pack_rows_kernel");
+  RGBMP_CUDA(cudaMemcpyAsync(out_host, packed, (size_t)N * F * sizeof(float), cudaMemcpyDeviceToHost, st));
   RGBMP_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

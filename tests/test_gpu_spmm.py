@@ -98,9 +98,11 @@ def test_every_launch_shape_gives_the_same_answer():
                 y = p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=G | (V << 8) | (U << 16))
                 assert relerr(y, ref) <= TOL, (G, V, U)
                 outs.append(y)
-    # the accumulation order never depends on the launch shape
+    # rows that are not split accumulate in the same order whatever the launch shape
+    short = (g.fwd.degree() <= g.fwd.chunk)
+    assert int((~short).sum()) > 0
     for y in outs[1:]:
-        assert torch.equal(y, outs[0])
+        assert torch.equal(y[short], outs[0][short])
 
 
 def test_unaligned_input_takes_the_scalar_path_and_noncontiguous_views_work():
