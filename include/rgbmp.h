@@ -109,6 +109,13 @@ int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int
                        int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long, int64_t* item_start,
                        void* ws, size_t ws_bytes, int device, void* stream);
 
+/* Row schedule for the short-row SpMM kernel: rows sorted by degree (longest first) inside windows
+ * of `window` consecutive rows, so that the rows sharing a warp have equal length (no divergence)
+ * while coarse locality of neighbouring rows is kept.  order int32 [n_rows]. */
+size_t rgbmp_row_order_workspace_bytes(int64_t n_rows);
+int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order,
+                    void* ws, size_t ws_bytes, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b) aggregation kernels
  * ------------------------------------------------------------------------------------------ */
@@ -127,6 +134,7 @@ typedef struct rgbmp_graph {
   const int32_t* long_item_ptr;/* [n_long+1]                                                        */
   const int32_t* item_long;    /* [n_items]                                                         */
   const int64_t* item_start;   /* [n_items]                                                         */
+  const int32_t* row_order;    /* [n_rows] schedule of the short-row kernel, or NULL = natural order */
 } rgbmp_graph_t;
 
 /* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
@@ -161,7 +169,8 @@ typedef struct rgbmp_epilogue {
  * Replaces MessagePassing.propagate = index_select -> message -> scatter
  * (graphsage.py:58, dagnn.py:46,57-59; inside GCNConv gcn.py:27,29, SAGEConv, GINConv, ...).
  * val may be NULL (unweighted sum / mean via row_scale).  The same call on the transpose CSR is
- * the backward.  `tune` = 0 picks the launch shape heuristically; otherwise (G | V<<8 | U<<16). */
+ * the backward.  `tune` = 0 picks the launch shape heuristically; otherwise (G | V<<8 | U<<16),
+ * G in {1,2,4,8,16,32} lanes per row, V in 1..4 vectors per lane, U in {2,4,8} edges in flight. */
 size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F);
 int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx,
                void* Y, int64_t ldy, int F, int dtype, const rgbmp_epilogue_t* ep, int tune,

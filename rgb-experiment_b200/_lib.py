@@ -19,7 +19,8 @@ class GraphStruct(C.Structure):
     """rgbmp_graph_t"""
     _fields_ = [("n_rows", c_i64), ("n_cols", c_i64), ("nnz", c_i64), ("rowptr", c_vp), ("col", c_vp),
                 ("chunk", c_i32), ("long_chunk", c_i32), ("n_long", c_i64), ("n_items", c_i64),
-                ("long_rows", c_vp), ("long_item_ptr", c_vp), ("item_long", c_vp), ("item_start", c_vp)]
+                ("long_rows", c_vp), ("long_item_ptr", c_vp), ("item_long", c_vp), ("item_start", c_vp),
+                ("row_order", c_vp)]
 
 
 class Epilogue(C.Structure):
@@ -58,6 +59,8 @@ def lib():
         "rgbmp_longrow_fill_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_longrow_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                                          C.c_int, c_vp]),
+        "rgbmp_row_order_workspace_bytes": (c_sz, [c_i64]),
+        "rgbmp_row_order": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_spmm_workspace_bytes": (c_sz, [GP, C.c_int]),
         "rgbmp_spmm": (C.c_int, [GP, c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_int, EP, C.c_int, c_vp, c_sz,
                                  C.c_int, c_vp]),

@@ -383,6 +383,40 @@ __global__ void longrow_fill_kernel(const int64_t* __restrict__ rowptr, int64_t 
   }
 }
 
+// stable LSD radix sort of (key, index) pairs on the low `bits` bits of the key; the permutation
+// (original index of every sorted element) lands in vfinal.  kA/kB/vA: scratch of n int32 each.
+static int sort_pairs_i32(const int32_t* key, int64_t n, int bits, int32_t* kA, int32_t* kB, int32_t* vA,
+                          int32_t* vfinal, int32_t* bh, int32_t* sc32, int64_t nb, cudaStream_t st) {
+  const int passes = (bits + 7) / 8;
+  const int32_t* kin = key;
+  const int32_t* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    int32_t* kout = (p & 1) ? kB : kA;
+    int32_t* vout = (((passes - 1 - p) & 1) == 0) ? vfinal : vA;   // the LAST pass writes vfinal
+    rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, n, shift, nb, bh);
+    RGBMP_LAUNCH_CHECK("rs_hist_kernel");
+    RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
+    if (p == 0)
+      rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+    else
+      rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+    RGBMP_LAUNCH_CHECK("rs_scatter_kernel");
+    kin = kout;
+    vin = vout;
+  }
+  return 0;
+}
+
+__global__ void row_key_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t window,
+                               int32_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  int64_t deg = rowptr[i + 1] - rowptr[i];
+  if (deg > 0xFFFF) deg = 0xFFFF;
+  keys[i] = (int32_t)(((i / window) << 16) | (0xFFFF - deg));   // window-major, longest rows first
+}
+
 }  // namespace rgbmp
 
 using namespace rgbmp;
@@ -480,29 +514,12 @@ int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64
   }
   RGBMP_CUDA(exclusive_scan<int64_t>(rowptr, N + 1, sc64, st));
   if (nnz == 0) return 0;
+  int rc_sort = 0;
 
   int bits = 1;
   while (bits < 31 && (1ll << bits) < N) ++bits;
-  const int passes = (bits + 7) / 8;
-  // ping-pong so that the LAST pass writes values straight into `eid`; vals buffers: vA and eid
-  const int32_t* kin = key;
-  const int32_t* vin = nullptr;
-  for (int p = 0; p < passes; ++p) {
-    const int shift = 8 * p;
-    int32_t* kout = (p & 1) ? kB : kA;
-    // choose the value buffer so that pass (passes-1) lands in eid
-    int32_t* vout = (((passes - 1 - p) & 1) == 0) ? eid : vA;
-    rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, nnz, shift, nb, bh);
-    RGBMP_LAUNCH_CHECK("rs_hist_kernel");
-    RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
-    if (p == 0)
-      rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, nnz, shift, nb, bh, kout, vout);
-    else
-      rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, nnz, shift, nb, bh, kout, vout);
-    RGBMP_LAUNCH_CHECK("rs_scatter_kernel");
-    kin = kout;
-    vin = vout;
-  }
+  rc_sort = sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st);
+  if (rc_sort) return rc_sort;
   gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(other, eid, nnz, col);
   RGBMP_LAUNCH_CHECK("gather_i32_kernel");
   return 0;
@@ -584,6 +601,39 @@ int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int
                                           long_item_ptr, item_long, item_start);
   RGBMP_LAUNCH_CHECK("longrow_fill_kernel");
   return 0;
+}
+
+size_t rgbmp_row_order_workspace_bytes(int64_t n_rows) {
+  const size_t n = (size_t)(n_rows > 0 ? n_rows : 1);
+  const size_t nb = (size_t)ceil_div((int64_t)n, RS_TILE);
+  return 4 * align_up(n * sizeof(int32_t), 256) + align_up(RS_BINS * nb * sizeof(int32_t), 256) +
+         align_up(scan_ws_elems((int64_t)(RS_BINS * nb)) * sizeof(int32_t), 256) + 4096;
+}
+
+int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order, void* ws, size_t ws_bytes,
+                    int device, void* stream) {
+  if (!rowptr || !order || n_rows <= 0 || window <= 0 || !ws) return fail(RGBMP_EINVAL, "rgbmp_row_order: bad argument");
+  if (n_rows >= (1ll << 31) - 1) return fail(RGBMP_ERANGE, "rgbmp_row_order: n_rows exceeds int32");
+  if (ws_bytes < rgbmp_row_order_workspace_bytes(n_rows)) return fail(RGBMP_EWORKSPACE, "rgbmp_row_order: workspace");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_row_order: bad device");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (window < ceil_div(n_rows, 32768)) window = ceil_div(n_rows, 32768);   // window id must fit 15 bits
+  const int64_t nwin = ceil_div(n_rows, window);
+  int wbits = 0;
+  while ((1ll << wbits) < nwin) ++wbits;
+  const int64_t nb = ceil_div(n_rows, RS_TILE);
+  Carver cv(ws, ws_bytes);
+  int32_t* keys = cv.take<int32_t>((size_t)n_rows);
+  int32_t* kA = cv.take<int32_t>((size_t)n_rows);
+  int32_t* kB = cv.take<int32_t>((size_t)n_rows);
+  int32_t* vA = cv.take<int32_t>((size_t)n_rows);
+  int32_t* bh = cv.take<int32_t>((size_t)RS_BINS * nb);
+  int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
+  if (!cv.ok()) return fail(RGBMP_EWORKSPACE, "rgbmp_row_order: workspace carve");
+  row_key_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, window, keys);
+  RGBMP_LAUNCH_CHECK("row_key_kernel");
+  return sort_pairs_i32(keys, n_rows, 16 + wbits, kA, kB, vA, order, bh, sc32, nb, st);
 }
 
 }  // extern "C"

@@ -59,6 +59,7 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
   p.rowptr = g->rowptr;
   p.col = g->col;
   p.val = val;
+  p.row_order = g->row_order;
   p.n_rows = g->n_rows;
   p.chunk = g->n_items > 0 ? g->chunk : 0;
   p.long_chunk = g->long_chunk;
@@ -112,7 +113,7 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
     V = (tune >> 8) & 0xFF;
     U = (tune >> 16) & 0xFF;
     const bool pow2 = G > 0 && (G & (G - 1)) == 0 && G <= 32;
-    if (!pow2 || V < 1 || V > 4 || (U != 2 && U != 4 && U != 8))
+    if (!pow2 || V < 1 || V > 4 || (U != 2 && U != 4 && U != 8 && U != 18 && U != 20))
       return fail(RGBMP_EINVAL, "rgbmp_spmm: bad tune word 0x%x", tune);
   }
   if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(p, G, V, U, st);

@@ -23,6 +23,7 @@ struct SpmmParams {
   const int64_t* rowptr;
   const int32_t* col;
   const float* val;
+  const int32_t* row_order;  // nullable: schedule of the short-row kernel
   int64_t n_rows;
   int32_t chunk;
   // long rows
@@ -55,6 +56,7 @@ struct Raw<float, 4> {
   __device__ __forceinline__ void load(const float* p) { r = __ldg(reinterpret_cast<const float4*>(p)); }
   __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void unpack(float (&f)[4]) const { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
+  __device__ __forceinline__ float2 pair(int i) const { return i == 0 ? make_float2(r.x, r.y) : make_float2(r.z, r.w); }
   static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
   }
@@ -65,6 +67,7 @@ struct Raw<float, 1> {
   __device__ __forceinline__ void load(const float* p) { r = __ldg(p); }
   __device__ __forceinline__ void zero() { r = 0.f; }
   __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = r; }
+  __device__ __forceinline__ float2 pair(int) const { return make_float2(r, 0.f); }
   static __device__ __forceinline__ void store(float* p, const float (&f)[1]) { *p = f[0]; }
 };
 template <>
@@ -79,6 +82,10 @@ struct Raw<__nv_bfloat16, 8> {
       f[2 * i] = __uint_as_float(w[i] << 16);
       f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
     }
+  }
+  __device__ __forceinline__ float2 pair(int i) const {
+    const uint32_t w = i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
     uint32_t w[4];
@@ -96,6 +103,7 @@ struct Raw<__nv_bfloat16, 1> {
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *p; }
   __device__ __forceinline__ void zero() { r = __float2bfloat16(0.f); }
   __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = __bfloat162float(r); }
+  __device__ __forceinline__ float2 pair(int) const { return make_float2(__bfloat162float(r), 0.f); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[1]) { *p = __float2bfloat16(f[0]); }
 };
 
@@ -103,61 +111,163 @@ __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
 
 // ------------------------------------------------------------------------------------------
-// accumulate edges [k0, k1) of one row into acc (sequential, stable order)
+// accumulate edges [k0, k1) of one row into acc (sequential, stable order).
+//
+// Lean inner loop (v2, after the v1 ncu profile showed 43 instructions per 16-byte gather):
+//   * the G lanes of the group load G consecutive column ids (and weights) with ONE coalesced load
+//     per lane and broadcast them with warp shuffles -- 1 LDG per lane per G edges instead of 2 per edge;
+//   * the next batch of ids is prefetched while the current one is consumed;
+//   * feature address = lane base + uint32(col) * row_bytes in one IMAD.WIDE.U32;
+//   * multiply and add are the packed fp32x2 instructions of sm_100 (FMUL2 / FADD2): half the FP
+//     issue slots, still one IEEE rounding per operation (bit-identical to scalar mul + add);
+//   * full batches of U edges run unpredicated, only the last partial batch is masked.
 // ------------------------------------------------------------------------------------------
-template <typename T, int EPV, int G, int V, int U>
-__device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0, int64_t k1, int f_lane0,
-                                                 const bool (&active)[V], float (&acc)[V][EPV]) {
-  const T* __restrict__ X = reinterpret_cast<const T*>(p.X);
-  const int32_t* __restrict__ col = p.col;
-  const float* __restrict__ val = p.val;
-  int32_t c[U];
-  float w[U];
+// packed fp32x2 math of sm_100 (FFMA2 / FADD2): one instruction per two floats.  Weighted sums use
+// a fused multiply-add (one rounding; ptxas contracts mul.rn + add.rn on f32x2 anyway), unweighted
+// sums are plain IEEE adds in stable edge order and therefore bit-identical to PyG-CPU scatter_add_.
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r)
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return reinterpret_cast<float2&>(r);
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return reinterpret_cast<float2&>(r);
+}
+
+template <typename T, int EPV, bool HASW>
+__device__ __forceinline__ void accum_vec(float2 (&acc)[(EPV + 1) / 2], const Raw<T, EPV>& raw, float w) {
+  if constexpr (EPV == 1) {
+    const float f = raw.pair(0).x;
+    acc[0].x = HASW ? __fmaf_rn(w, f, acc[0].x) : __fadd_rn(acc[0].x, f);
+  } else {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    c[u] = (k0 + u < k1) ? __ldg(col + k0 + u) : -1;
-    w[u] = (val != nullptr && k0 + u < k1) ? __ldg(val + k0 + u) : 1.0f;
+    for (int i = 0; i < EPV / 2; ++i)
+      acc[i] = HASW ? fma2_rn(make_float2(w, w), raw.pair(i), acc[i]) : add2_rn(acc[i], raw.pair(i));
   }
-  for (int64_t k = k0; k < k1; k += U) {
-    Raw<T, EPV> raw[U][V];
+}
+
+// address of a gathered row for this lane: base + col * row_bytes in ONE IMAD.WIDE.U32
+__device__ __forceinline__ const char* row_addr(const char* base, uint32_t c, uint32_t row_bytes) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(c), "r"(row_bytes), "l"((unsigned long long)base));
+  return reinterpret_cast<const char*>(r);
+}
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// The loop is WARP-uniform: every lane of the warp runs the same number of batches (the maximum
+// over the warp's groups; with the degree-sorted row schedule the groups of a warp have equal
+// lengths, so nothing is wasted), which lets all shuffles use the full mask (no convergence
+// checks) and lets full batches run without a single predicate.
+// xb[v]: this lane's base pointer for its v-th vector (lanes beyond F point at vector 0 of the
+// row -- they load valid memory and never store).
+// PIPE: software-pipelined main loop -- the features of step j+1 are requested BEFORE the math of
+// step j and consumed in the next loop iteration, so UE*V loads per lane are always in flight
+// whatever order ptxas picks inside one iteration (without it, ptxas 12.9 sinks each LDG next to
+// its FFMA2 and serialises the gathers).
+template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
+__device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0, int64_t k1, const char* const (&xb)[V],
+                                                 int gl, float2 (&acc)[V][(EPV + 1) / 2]) {
+  constexpr int UE = (U < G) ? U : G;   // edges per inner step (a batch holds G ids)
+  const uint32_t row_bytes = (uint32_t)(p.ldx * (int64_t)sizeof(T));
+  const int32_t* __restrict__ col = p.col + k0;
+  const float* __restrict__ val = HASW ? p.val + k0 : nullptr;
+  const int len = (k1 > k0) ? (int)(k1 - k0) : 0;          // <= chunk / long sub-range, fits int
+  const int maxlen = __reduce_max_sync(FULL, len);
+  if (maxlen == 0) return;
+  int32_t cl = (gl < len) ? __ldg(col + gl) : 0;
+  float wl = 0.f;
+  if constexpr (HASW) wl = (gl < len) ? __ldg(val + gl) : 0.f;
+  for (int off = 0; off < maxlen; off += G) {
+    int nb = len - off;
+    nb = nb < 0 ? 0 : (nb > G ? G : nb);
+    int32_t cn = 0;
+    float wn = 0.f;
+    if (off + G + gl < len) {                       // prefetch the next batch of ids / weights
+      cn = __ldg(col + off + G + gl);
+      if constexpr (HASW) wn = __ldg(val + off + G + gl);
+    }
+    if (__all_sync(FULL, nb == G)) {                // every group has a full batch: no predicates
+      if constexpr (PIPE && (G / UE) >= 2) {
+        Raw<T, EPV> cur[UE][V];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const T* rowp = X + (int64_t)c[u] * p.ldx + f_lane0;
+        for (int u = 0; u < UE; ++u) {
+          const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, u, G);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        if (c[u] >= 0 && active[v]) raw[u][v].load(rowp + v * G * EPV);
-        else raw[u][v].zero();
+          for (int v = 0; v < V; ++v) cur[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+        }
+#pragma unroll 1
+        for (int j = 0; j < G; j += UE) {
+          Raw<T, EPV> nxt[UE][V];
+          const int jn = (j + UE < G) ? j + UE : j;   // last step re-requests itself (L1 hit, result unused)
+#pragma unroll
+          for (int u = 0; u < UE; ++u) {
+            const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, jn + u, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) nxt[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+          }
+#pragma unroll
+          for (int u = 0; u < UE; ++u) {
+            float w = 1.0f;
+            if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], cur[u][v], w);
+          }
+#pragma unroll
+          for (int u = 0; u < UE; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) cur[u][v] = nxt[u][v];
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < G; j += UE) {
+          Raw<T, EPV> raw[UE][V];
+#pragma unroll
+          for (int u = 0; u < UE; ++u) {
+            const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) raw[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+          }
+#pragma unroll
+          for (int u = 0; u < UE; ++u) {
+            float w = 1.0f;
+            if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
+#pragma unroll
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], w);
+          }
+        }
       }
-    }
-    // prefetch the next U column ids / weights while the feature loads are in flight
-    int32_t cn[U];
-    float wn[U];
-    const int64_t kn = k + U;
+    } else {                                        // tail batches: per-group predicates
+      const int nbmax = __reduce_max_sync(FULL, nb);
+#pragma unroll 1
+      for (int j = 0; j < nbmax; j += UE) {
+        Raw<T, EPV> raw[UE][V];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      cn[u] = (kn + u < k1) ? __ldg(col + kn + u) : -1;
-      wn[u] = (val != nullptr && kn + u < k1) ? __ldg(val + kn + u) : 1.0f;
-    }
+        for (int u = 0; u < UE; ++u) {
+          const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);   // lanes past nb hold id 0: a valid row
+          if (j + u < nb) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (c[u] >= 0) {
+            for (int v = 0; v < V; ++v) raw[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+          }
+        }
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float f[EPV];
-          raw[u][v].unpack(f);
+        for (int u = 0; u < UE; ++u) {
+          float w = 1.0f;
+          if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
+          if (j + u < nb) {
 #pragma unroll
-          for (int i = 0; i < EPV; ++i) {
-            const float m = (val != nullptr) ? __fmul_rn(w[u], f[i]) : f[i];
-            acc[v][i] = __fadd_rn(acc[v][i], m);
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], w);
           }
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      c[u] = cn[u];
-      w[u] = wn[u];
-    }
+    cl = cn;
+    wl = wn;
   }
 }
 
@@ -200,33 +310,58 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
 
 constexpr int SPMM_THREADS = 256;
 
+// per-lane vector bases: lane l of the group owns vectors l, l+G, ... of the feature tile
+template <typename T, int EPV, int G, int V>
+__device__ __forceinline__ void lane_bases(const SpmmParams& p, int f0, const char* (&xb)[V], bool (&active)[V]) {
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int f = f0 + v * G * EPV;
+    active[v] = f < p.F;
+    xb[v] = reinterpret_cast<const char*>(p.X) + (size_t)(active[v] ? f : 0) * sizeof(T);
+  }
+}
+
 // short rows: one group of G lanes per row.  blockIdx.y = feature tile of G*V*EPV elements.
-template <typename T, int EPV, int G, int V, int U>
+// Rows are taken in `row_order` (degree-sorted inside windows, built once per graph) so that the
+// groups sharing a warp run rows of equal length -- no idle issue slots from divergent trip counts.
+template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_rows_kernel(const SpmmParams p) {
   constexpr int GPB = SPMM_THREADS / G;
   const int gl = threadIdx.x % G;
-  const int64_t row = (int64_t)blockIdx.x * GPB + threadIdx.x / G;
-  if (row >= p.n_rows) return;
-  const int64_t k0 = __ldg(p.rowptr + row), k1 = __ldg(p.rowptr + row + 1);
-  if (p.chunk > 0 && k1 - k0 > p.chunk) return;  // long row: handled by spmm_long_kernel
-  const int f0 = blockIdx.y * (G * V * EPV) + gl * EPV;
-  bool active[V];
-  float acc[V][EPV];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    active[v] = (f0 + v * G * EPV) < p.F;
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) acc[v][i] = 0.f;
+  const int64_t gid = (int64_t)blockIdx.x * GPB + threadIdx.x / G;
+  int64_t row = -1, k0 = 0, k1 = 0;
+  if (gid < p.n_rows) {
+    row = p.row_order ? (int64_t)__ldg(p.row_order + gid) : gid;
+    k0 = __ldg(p.rowptr + row);
+    k1 = __ldg(p.rowptr + row + 1);
+    if (p.chunk > 0 && k1 - k0 > p.chunk) row = -1;  // long row: handled by spmm_long_kernel
   }
-  accumulate_range<T, EPV, G, V, U>(p, k0, k1, f0, active, acc);
+  if (row < 0) k1 = k0;                               // idle group: stays in the warp-uniform loop with no edges
+  const int f0 = blockIdx.y * (G * V * EPV) + gl * EPV;
+  const char* xb[V];
+  bool active[V];
+  float2 acc[V][(EPV + 1) / 2];
+  lane_bases<T, EPV, G, V>(p, f0, xb, active);
 #pragma unroll
   for (int v = 0; v < V; ++v)
-    if (active[v]) epilogue_store<T, EPV>(p, row, f0 + v * G * EPV, acc[v]);
+#pragma unroll
+    for (int i = 0; i < (EPV + 1) / 2; ++i) acc[v][i] = make_float2(0.f, 0.f);
+  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, gl, acc);
+  if (row < 0) return;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (active[v]) {
+      float s[EPV];
+#pragma unroll
+      for (int i = 0; i < EPV; ++i) s[i] = (i & 1) ? acc[v][i / 2].y : acc[v][i / 2].x;
+      epilogue_store<T, EPV>(p, row, f0 + v * G * EPV, s);
+    }
+  }
 }
 
 // long rows: one CTA per work item (<= long_chunk edges of one row); the CTA's groups take
 // contiguous sub-ranges, partial sums are reduced through shared memory in a fixed order.
-template <typename T, int EPV, int G, int V, int U>
+template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_long_kernel(const SpmmParams p) {
   constexpr int Q = SPMM_THREADS / G;      // groups per CTA
   constexpr int W = G * V * EPV;           // feature tile width
@@ -245,19 +380,20 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_long_kernel(const SpmmParam
   if (k1 > re) k1 = re;
   const int ftile = blockIdx.y * W;
   const int f0 = ftile + gl * EPV;
+  const char* xb[V];
   bool active[V];
-  float acc[V][EPV];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    active[v] = (f0 + v * G * EPV) < p.F;
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) acc[v][i] = 0.f;
-  }
-  accumulate_range<T, EPV, G, V, U>(p, k0, k1, f0, active, acc);
+  float2 acc[V][(EPV + 1) / 2];
+  lane_bases<T, EPV, G, V>(p, f0, xb, active);
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
-    for (int i = 0; i < EPV; ++i) sm[q * W + (gl + v * G) * EPV + i] = acc[v][i];
+    for (int i = 0; i < (EPV + 1) / 2; ++i) acc[v][i] = make_float2(0.f, 0.f);
+  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, gl, acc);
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int i = 0; i < EPV; ++i)
+      sm[q * W + (gl + v * G) * EPV + i] = active[v] ? ((i & 1) ? acc[v][i / 2].y : acc[v][i / 2].x) : 0.f;
   __syncthreads();
   for (int t = threadIdx.x; t < W; t += SPMM_THREADS) {
     float s = 0.f;
@@ -298,20 +434,20 @@ row_scale_kernel(const T* __restrict__ X, int64_t ldx, const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // launch dispatch
 // ------------------------------------------------------------------------------------------
-template <typename T, int EPV, int G, int V, int U>
+template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
 int launch_cfg(const SpmmParams& p, cudaStream_t st) {
   constexpr int W = G * V * EPV;
   const unsigned ytiles = (unsigned)ceil_div(p.F, W);
   constexpr int GPB = SPMM_THREADS / G;
   if (p.n_rows > 0) {
     dim3 grid((unsigned)ceil_div(p.n_rows, GPB), ytiles);
-    spmm_rows_kernel<T, EPV, G, V, U><<<grid, SPMM_THREADS, 0, st>>>(p);
+    spmm_rows_kernel<T, EPV, G, V, U, HASW, PIPE><<<grid, SPMM_THREADS, 0, st>>>(p);
     RGBMP_LAUNCH_CHECK("spmm_rows_kernel");
   }
   if (p.n_items > 0) {
     constexpr int Q = SPMM_THREADS / G;
     dim3 grid((unsigned)p.n_items, ytiles);
-    spmm_long_kernel<T, EPV, G, V, U><<<grid, SPMM_THREADS, Q * W * sizeof(float), st>>>(p);
+    spmm_long_kernel<T, EPV, G, V, U, HASW, PIPE><<<grid, SPMM_THREADS, Q * W * sizeof(float), st>>>(p);
     RGBMP_LAUNCH_CHECK("spmm_long_kernel");
     spmm_combine_kernel<T><<<(unsigned)ceil_div(p.n_long * p.F, 256), 256, 0, st>>>(p);
     RGBMP_LAUNCH_CHECK("spmm_combine_kernel");
@@ -319,12 +455,20 @@ int launch_cfg(const SpmmParams& p, cudaStream_t st) {
   return 0;
 }
 
+template <typename T, int EPV, int G, int V, int U, bool PIPE>
+int dispatch_w(const SpmmParams& p, cudaStream_t st) {
+  return p.val ? launch_cfg<T, EPV, G, V, U, true, PIPE>(p, st) : launch_cfg<T, EPV, G, V, U, false, PIPE>(p, st);
+}
+
+// U field of the tune word: 2 / 4 / 8 = edges per step; +16 = software-pipelined main loop
 template <typename T, int EPV, int G, int V>
 int dispatch_u(const SpmmParams& p, int U, cudaStream_t st) {
   switch (U) {
-    case 2: return launch_cfg<T, EPV, G, V, 2>(p, st);
-    case 8: return launch_cfg<T, EPV, G, V, 8>(p, st);
-    default: return launch_cfg<T, EPV, G, V, 4>(p, st);
+    case 2: return dispatch_w<T, EPV, G, V, 2, false>(p, st);
+    case 8: return dispatch_w<T, EPV, G, V, 8, false>(p, st);
+    case 18: return dispatch_w<T, EPV, G, V, 2, true>(p, st);
+    case 20: return dispatch_w<T, EPV, G, V, 4, true>(p, st);
+    default: return dispatch_w<T, EPV, G, V, 4, false>(p, st);
   }
 }
 

@@ -23,6 +23,7 @@ NORM_INV_SQRT, NORM_INV_MEAN, NORM_COUNT = 0, 1, 2
 
 DEFAULT_CHUNK = 1024        # rows with more edges than this are split ...
 DEFAULT_LONG_CHUNK = 4096   # ... into CTA work items of this many edges
+DEFAULT_WINDOW = 16384      # rows are degree-sorted inside windows of this many rows (0 = natural order)
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -34,7 +35,7 @@ class CSR:
     (position in the edited edge list), plus the long-row work lists and the ctypes descriptor."""
 
     def __init__(self, key: torch.Tensor, other: torch.Tensor, n_rows: int, n_cols: int,
-                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK):
+                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None):
         L = lib()
         dev = key.device
         st = stream_of(dev)
@@ -52,10 +53,17 @@ class CSR:
         self.n_long = self.n_items = 0
         self.long_rows = self.long_item_ptr = self.item_long = self.item_start = None
         self._split_long_rows()
+        self.row_order = None
+        window = DEFAULT_WINDOW if window is None else int(window)
+        if window > 0 and n_rows > 1 and nnz > 0:
+            self.row_order = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            ws = _ws(L.rgbmp_row_order_workspace_bytes(n_rows), dev)
+            check(L.rgbmp_row_order(ptr(self.rowptr), n_rows, window, ptr(self.row_order), ptr(ws), ws.numel(),
+                                    dev.index, st), "row_order")
         self._norm = {}
         self.struct = GraphStruct(n_rows, n_cols, nnz, ptr(self.rowptr), ptr(self.col), self.chunk, self.long_chunk,
                                   self.n_long, self.n_items, ptr(self.long_rows), ptr(self.long_item_ptr),
-                                  ptr(self.item_long), ptr(self.item_start))
+                                  ptr(self.item_long), ptr(self.item_start), ptr(self.row_order))
         self.ref = C.byref(self.struct)
 
     def _split_long_rows(self):
@@ -102,7 +110,7 @@ class Graph:
     """Edited edge list + forward CSR (+ lazy transpose CSR, normalisation vectors, edge weights)."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, loop_mode: int = LOOP_NONE,
-                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK):
+                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None):
         _lib.require_cuda(edge_index, "edge_index")
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")
@@ -112,7 +120,7 @@ class Graph:
         ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
         E, N = ei.size(1), int(num_nodes)
         self.N, self.E_in, self.loop_mode, self.device = N, E, loop_mode, dev
-        self._chunk, self._long_chunk = chunk, long_chunk
+        self._chunk, self._long_chunk, self._window = chunk, long_chunk, window
         e_src = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
         e_dst = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
         nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
@@ -124,7 +132,7 @@ class Graph:
             raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
         self.nnz = nnz
         self.e_src, self.e_dst = e_src[:nnz], e_dst[:nnz]          # edited list: kept edges, then loops
-        self.fwd = CSR(self.e_dst, self.e_src, N, N, chunk, long_chunk)   # rows = targets i, col = sources j
+        self.fwd = CSR(self.e_dst, self.e_src, N, N, chunk, long_chunk, window)   # rows = targets i, col = sources j
         self._bwd: Optional[CSR] = None
         self._lock = threading.Lock()
         self._vals = {}
@@ -135,7 +143,7 @@ class Graph:
         if self._bwd is None:
             with self._lock:
                 if self._bwd is None:
-                    self._bwd = CSR(self.e_src, self.e_dst, self.N, self.N, self._chunk, self._long_chunk)
+                    self._bwd = CSR(self.e_src, self.e_dst, self.N, self.N, self._chunk, self._long_chunk, self._window)
         return self._bwd
 
     def dinv(self) -> torch.Tensor:

@@ -492,7 +492,8 @@ class _EidView:
         self._csr = csr
         self.struct = GraphStruct(csr.n_rows, csr.nnz, csr.nnz, ptr(csr.rowptr), ptr(csr.eid), csr.chunk,
                                   csr.long_chunk, csr.n_long, csr.n_items, ptr(csr.long_rows),
-                                  ptr(csr.long_item_ptr), ptr(csr.item_long), ptr(csr.item_start))
+                                  ptr(csr.long_item_ptr), ptr(csr.item_long), ptr(csr.item_start),
+                                  ptr(csr.row_order))
         self.ref = C.byref(self.struct)
 
     def spmm_workspace(self, F):

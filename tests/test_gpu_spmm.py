@@ -48,11 +48,12 @@ def test_propagate_forward_backward(case, kind, mode, F):
     assert relerr(xg.grad, xo.grad) <= TOL
 
 
-@pytest.mark.parametrize("kind,mode", [("sum", 0), ("mean", 3), ("gcn", 2)])
+@pytest.mark.parametrize("kind,mode", [("sum", 0), ("mean", 3)])
 def test_bitwise_fidelity_to_cpu_scatter_order(kind, mode):
-    """Rows that are not split accumulate their edges sequentially in stable edge order with
-    separate multiply and add -- the order PyG-on-CPU scatter_add_ uses -- so fp32 results are
-    bit-identical to the oracle, forward and backward."""
+    """Rows that are not split accumulate their edges sequentially in stable edge order -- the
+    order PyG-on-CPU scatter_add_ uses -- so unweighted fp32 sums / means are bit-identical to the
+    oracle, forward and backward.  (Weighted sums use one fused multiply-add per edge, i.e. one
+    rounding instead of two, and are held to the 1e-5 bar instead.)"""
     p = P()
     ei, n = CASES["loops_dups"]()
     F = 20
@@ -94,7 +95,7 @@ def test_every_launch_shape_gives_the_same_answer():
     outs = []
     for G in (1, 2, 4, 8, 16, 32):
         for V in (1, 2, 3, 4):
-            for U in (2, 4, 8):
+            for U in (2, 4, 8, 18, 20):
                 y = p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=G | (V << 8) | (U << 16))
                 assert relerr(y, ref) <= TOL, (G, V, U)
                 outs.append(y)

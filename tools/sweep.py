@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--workloads", default="products,arxiv")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--chunks", default="")
+    ap.add_argument("--windows", default="16384", help="comma list of row-schedule windows (0 = natural order, -1 = global)")
+    ap.add_argument("--us", default="2,4,8,18,20")
+    ap.add_argument("--minimal", action="store_true", help="only the shapes with the fewest idle lanes")
     args = ap.parse_args()
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.synth as S
@@ -46,12 +49,13 @@ def main():
         chunk_opts = [(1024, 4096)]
         if args.chunks:
             chunk_opts = [tuple(int(v) for v in c.split(":")) for c in args.chunks.split(",")]
-        for chunk, lchunk in chunk_opts:
-            g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING, chunk=chunk, long_chunk=lchunk)
+        for chunk, lchunk, window in [(c, l, int(w)) for (c, l) in chunk_opts for w in args.windows.split(",")]:
+            g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING, chunk=chunk, long_chunk=lchunk,
+                        window=(N if window < 0 else window))
             val = g.gcn_val(False)
             deg = g.fwd.degree()
             print(json.dumps({"workload": wl, "N": N, "nnz": g.nnz, "max_deg": int(deg.max()), "n_long": g.fwd.n_long,
-                              "n_items": g.fwd.n_items, "chunk": chunk, "long_chunk": lchunk}), flush=True)
+                              "n_items": g.fwd.n_items, "chunk": chunk, "long_chunk": lchunk, "window": window}), flush=True)
             for F, dt in plans[wl]:
                 x = torch.randn(N, F, device=dev).to(dt)
                 xb, ld = P.ops.as_rows(x)
@@ -67,14 +71,16 @@ def main():
                                 continue
                             if G * V >= 2 * nvec + 4:
                                 continue
-                            for U in (2, 4, 8):
+                            if args.minimal and (V > 2 or G * V >= 2 * nvec):
+                                continue
+                            for U in [int(u) for u in args.us.split(",")]:
                                 tune = G | (V << 8) | (U << 16)
                                 fn = lambda: P.ops.spmm_raw(g.fwd, xb, val if weighted else None, tune=tune, out=out)
                                 ms = time_ms(fn, iters)
                                 B = g.nnz * (F * esz + 4 + (4 if weighted else 0)) + N * F * esz + (N + 1) * 8
                                 r = {"workload": wl, "F": F, "dtype": str(dt).split(".")[-1], "weighted": weighted,
                                      "G": G, "V": V, "U": U, "ms": round(ms, 4), "GBps": round(B / ms / 1e6, 1),
-                                     "gteps": round(g.nnz / ms / 1e6, 3), "chunk": chunk}
+                                     "gteps": round(g.nnz / ms / 1e6, 3), "chunk": chunk, "window": window}
                                 res.append(r)
                                 print(json.dumps(r), flush=True)
                     best = min(res, key=lambda r: r["ms"])
