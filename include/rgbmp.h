@@ -116,6 +116,14 @@ size_t rgbmp_row_order_workspace_bytes(int64_t n_rows);
 int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order,
                     void* ws, size_t ws_bytes, int device, void* stream);
 
+/* Column popularity and hot tagging (no reference counterpart; it steers the L2 so that the
+ * feature rows gathered most often stay resident while once-touched rows stream through).
+ *   rgbmp_col_freq: freq[c] = number of entries with col[k] == c   (int32 [n_cols], zeroed here)
+ *   rgbmp_col_tag : out[k] = col[k] | (freq[col[k]] >= thresh ? 1u<<31 : 0) */
+int rgbmp_col_freq(const int32_t* col, int64_t nnz, int64_t n_cols, int32_t* freq, int device, void* stream);
+int rgbmp_col_tag(const int32_t* col, int64_t nnz, const int32_t* freq, int32_t thresh, int32_t* out,
+                  int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b) aggregation kernels
  * ------------------------------------------------------------------------------------------ */
@@ -135,6 +143,8 @@ typedef struct rgbmp_graph {
   const int32_t* item_long;    /* [n_items]                                                         */
   const int64_t* item_start;   /* [n_items]                                                         */
   const int32_t* row_order;    /* [n_rows] schedule of the short-row kernel, or NULL = natural order */
+  int32_t        col_tagged;   /* 1: bit 31 of col[k] marks a frequently gathered ("hot") column, see
+                                  rgbmp_col_tag; only rgbmp_spmm / rgbmp_khop / rgbmp_gat_* accept it      */
 } rgbmp_graph_t;
 
 /* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
@@ -170,7 +180,14 @@ typedef struct rgbmp_epilogue {
  * (graphsage.py:58, dagnn.py:46,57-59; inside GCNConv gcn.py:27,29, SAGEConv, GINConv, ...).
  * val may be NULL (unweighted sum / mean via row_scale).  The same call on the transpose CSR is
  * the backward.  `tune` = 0 picks the launch shape heuristically; otherwise (G | V<<8 | U<<16),
- * G in {1,2,4,8,16,32} lanes per row, V in 1..4 vectors per lane, U in {2,4,8} edges in flight. */
+ * G in {1,2,4,8,16,32} lanes per row, V in 1..4 vectors per lane, U in {2,4,8} edges in flight
+ * (+16: software-pipelined loop).  RGBMP_TUNE_NO_STREAM (may be or-ed into 0 too) turns off the
+ * evict-first cache policy on the once-touched streams (column ids, weights, teleport, output). */
+#define RGBMP_TUNE_NO_STREAM (1 << 24)
+/* L2 eviction priority of the gathered feature rows, for experiments: or RGBMP_TUNE_POLICY with
+ * (cold << 25) | (hot << 27), each 0 = normal, 1 = evict-first, 2 = evict-last.  Default: hot ids
+ * (bit 31 set by rgbmp_col_tag) evict-last and the rest evict-first on a tagged graph, normal otherwise. */
+#define RGBMP_TUNE_POLICY    (1 << 29)
 size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F);
 int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx,
                void* Y, int64_t ldy, int F, int dtype, const rgbmp_epilogue_t* ep, int tune,
@@ -211,17 +228,18 @@ int rgbmp_gat_forward(const rgbmp_graph_t* g, const float* Xp, int64_t ldx,
                       const float* drop, float* out, int64_t ldo, float* rowmax, float* rowsum,
                       void* ws, size_t ws_bytes, int device, void* stream);
 
-/* Backward on the TRANSPOSE CSR gT (rows = sources j).  S[i,h] = <dout[i,h,:], out[i,h,:]> is
- * computed by rgbmp_rowdot.  Writes dXp [n_src,H*C], da_src [n_src,H]; accumulates da_dst
- * [n_dst,H] (must be zero on entry).  eid_map_T: for drop (CSR order) lookup, tpos[k'] gives the
+/* Backward on the TRANSPOSE CSR gT (rows = sources j).  `out` is the forward result (the softmax
+ * backward needs S[i,h] = <dout[i,h,:], out[i,h,:]>, computed inside).  Writes dXp [n_src,H*C],
+ * da_src [n_src,H]; accumulates da_dst [n_dst,H] (must be zero on entry).  eid_map_T: for drop (CSR order) lookup, tpos[k'] gives the
  * forward-CSR position of transpose entry k' (NULL when drop is NULL). */
+size_t rgbmp_gat_backward_workspace_bytes(const rgbmp_graph_t* gT, int64_t n_dst, int H, int C);
 int rgbmp_gat_backward(const rgbmp_graph_t* gT, const float* Xp, int64_t ldx,
                        const float* a_src, const float* a_dst, int H, int C, float slope,
                        const float* drop, const int32_t* tpos,
-                       const float* rowmax, const float* rowsum, const float* S,
+                       const float* rowmax, const float* rowsum, const float* out, int64_t ldo,
                        const float* dout, int64_t ldd,
-                       float* dXp, int64_t lddx, float* da_src, float* da_dst,
-                       int device, void* stream);
+                       float* dXp, int64_t lddx, float* da_src, float* da_dst, int64_t n_dst,
+                       void* ws, size_t ws_bytes, int device, void* stream);
 
 /* S[i,h] = sum_c A[i,h*C+c]*B[i,h*C+c] */
 int rgbmp_rowdot(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n_rows,

@@ -20,7 +20,7 @@ class GraphStruct(C.Structure):
     _fields_ = [("n_rows", c_i64), ("n_cols", c_i64), ("nnz", c_i64), ("rowptr", c_vp), ("col", c_vp),
                 ("chunk", c_i32), ("long_chunk", c_i32), ("n_long", c_i64), ("n_items", c_i64),
                 ("long_rows", c_vp), ("long_item_ptr", c_vp), ("item_long", c_vp), ("item_start", c_vp),
-                ("row_order", c_vp)]
+                ("row_order", c_vp), ("col_tagged", c_i32)]
 
 
 class Epilogue(C.Structure):
@@ -74,8 +74,12 @@ def lib():
         "rgbmp_gat_workspace_bytes": (c_sz, [GP, C.c_int, C.c_int]),
         "rgbmp_gat_forward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_i64, c_vp,
                                         c_vp, c_vp, c_sz, C.c_int, c_vp]),
+        "rgbmp_gat_backward_workspace_bytes": (c_sz, [GP, c_i64, C.c_int, C.c_int]),
         "rgbmp_gat_backward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
-                                         c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, C.c_int, c_vp]),
+                                         c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
+                                         C.c_int, c_vp]),
+        "rgbmp_col_freq": (C.c_int, [c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp]),
+        "rgbmp_col_tag": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, C.c_int, c_vp]),
         "rgbmp_rowdot": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
         "rgbmp_sddmm": (C.c_int, [GP, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
         "rgbmp_u_add_v": (C.c_int, [GP, c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp]),

@@ -417,6 +417,23 @@ __global__ void row_key_kernel(const int64_t* __restrict__ rowptr, int64_t n_row
   keys[i] = (int32_t)(((i / window) << 16) | (0xFFFF - deg));   // window-major, longest rows first
 }
 
+__global__ void __launch_bounds__(256)
+col_freq_kernel(const int32_t* __restrict__ col, int64_t nnz, int32_t* __restrict__ freq) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
+    atomicAdd(freq + (col[k] & 0x7fffffff), 1);
+}
+
+__global__ void __launch_bounds__(256)
+col_tag_kernel(const int32_t* __restrict__ col, int64_t nnz, const int32_t* __restrict__ freq, int32_t thresh,
+               int32_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+    const int32_t c = col[k] & 0x7fffffff;
+    out[k] = (__ldg(freq + c) >= thresh) ? (int32_t)((uint32_t)c | 0x80000000u) : c;
+  }
+}
+
 }  // namespace rgbmp
 
 using namespace rgbmp;
@@ -634,6 +651,29 @@ int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32
   row_key_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, window, keys);
   RGBMP_LAUNCH_CHECK("row_key_kernel");
   return sort_pairs_i32(keys, n_rows, 16 + wbits, kA, kB, vA, order, bh, sc32, nb, st);
+}
+
+int rgbmp_col_freq(const int32_t* col, int64_t nnz, int64_t n_cols, int32_t* freq, int device, void* stream) {
+  if (nnz < 0 || n_cols < 0 || (nnz > 0 && !col) || (n_cols > 0 && !freq)) return fail(RGBMP_EINVAL, "rgbmp_col_freq: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_col_freq: bad device");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_cols > 0) RGBMP_CUDA(cudaMemsetAsync(freq, 0, (size_t)n_cols * sizeof(int32_t), st));
+  if (nnz == 0) return 0;
+  col_freq_kernel<<<kSMs * 16, 256, 0, st>>>(col, nnz, freq);
+  RGBMP_LAUNCH_CHECK("col_freq_kernel");
+  return 0;
+}
+
+int rgbmp_col_tag(const int32_t* col, int64_t nnz, const int32_t* freq, int32_t thresh, int32_t* out, int device,
+                  void* stream) {
+  if (nnz < 0 || (nnz > 0 && (!col || !freq || !out))) return fail(RGBMP_EINVAL, "rgbmp_col_tag: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_col_tag: bad device");
+  if (nnz == 0) return 0;
+  col_tag_kernel<<<kSMs * 16, 256, 0, (cudaStream_t)stream>>>(col, nnz, freq, thresh, out);
+  RGBMP_LAUNCH_CHECK("col_tag_kernel");
+  return 0;
 }
 
 }  // extern "C"

@@ -29,18 +29,27 @@ pack_rows_kernel(const float* __restrict__ X, int64_t ld, float* __restrict__ Y,
   }
 }
 
-// choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 (tools/sweep.py,
-// profiles/sweep_r01.txt): the fastest shapes keep V*U ~ 4 independent 16-byte loads in flight per
-// lane and give a row as many lanes as it has vectors (V = 1) -- wider groups coalesce better and
-// put fewer rows of different length in one warp; U = 8 or V >= 3 always lost (L1tex queueing).
-static void choose_shape(int nvec, int* G, int* V, int* U) {
-  if (nvec > 128) nvec = 128;  // wider rows are tiled over blockIdx.y
+// choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 with the v2 kernel and the
+// global degree-sorted row schedule (tools/sweep.py, profiles/r01_sweep_v2.txt):
+//   * two vectors per lane (V = 2) on half as many lanes beat V = 1 once the gathers come from HBM
+//     (products F=47: G8 V2 3.48 ms vs G16 V1 3.66 ms; F=100: G16 V2 7.06 vs G32 V1 7.64);
+//   * when the feature matrix is L2-resident (arxiv F=40 / bf16 F=128) V = 1 with 4 pipelined
+//     edges wins (0.148 vs 0.224 ms);
+//   * the software-pipelined loop (U = 18 / 20) wins nearly everywhere; V >= 3 and U = 8 never do;
+//   * rows wider than 64 vectors are tiled over blockIdx.y with G = 32, V = 2.
+static void choose_shape(int nvec, bool hbm_regime, int* G, int* V, int* U) {
+  if (nvec > 32) { *G = 32; *V = 2; *U = 20; return; }
+  if (nvec > 16) { *G = 16; *V = 2; *U = 18; return; }
+  if (nvec > 8) {
+    if (hbm_regime) { *G = 8; *V = 2; *U = 18; }
+    else { *G = 16; *V = 1; *U = 20; }
+    return;
+  }
   int g = 1;
-  while (g < nvec && g < 32) g <<= 1;
-  int v = (nvec + g - 1) / g;
+  while (g < nvec) g <<= 1;
   *G = g;
-  *V = v;
-  *U = (v <= 1) ? 4 : (v == 2 ? 4 : 2);
+  *V = 1;
+  *U = (g >= 4) ? 20 : 4;
 }
 
 static int check_graph(const rgbmp_graph_t* g, const char* fn) {
@@ -107,13 +116,25 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
 
   int G, V, U;
   const int nvec = (int)ceil_div(F, epv);
-  choose_shape(nvec, &G, &V, &U);
+  // gathered rows mostly come from HBM once the feature matrix is well beyond the 126 MB L2
+  const bool hbm_regime = (double)g->n_cols * (double)ldx * esz > 96e6;
+  choose_shape(nvec, hbm_regime, &G, &V, &U);
+  p.stream = (tune & RGBMP_TUNE_NO_STREAM) ? 0 : 1;
+  // gathered rows: ids tagged hot by rgbmp_col_tag stay in L2 (evict-last), the rest leave first
+  p.pol_hot = g->col_tagged ? 2 : 0;
+  p.pol_cold = g->col_tagged ? 1 : 0;
+  if (tune & RGBMP_TUNE_POLICY) {
+    p.pol_cold = (tune >> 25) & 3;
+    p.pol_hot = (tune >> 27) & 3;
+    if (p.pol_cold > 2 || p.pol_hot > 2) return fail(RGBMP_EINVAL, "rgbmp_spmm: bad cache policy in tune word 0x%x", tune);
+  }
+  tune &= 0xFFFFFF;
   if (tune != 0) {
     G = tune & 0xFF;
     V = (tune >> 8) & 0xFF;
     U = (tune >> 16) & 0xFF;
     const bool pow2 = G > 0 && (G & (G - 1)) == 0 && G <= 32;
-    if (!pow2 || V < 1 || V > 4 || (U != 2 && U != 4 && U != 8 && U != 18 && U != 20))
+    if (!pow2 || V < 1 || V > 2 || (U != 2 && U != 4 && U != 18 && U != 20))
       return fail(RGBMP_EINVAL, "rgbmp_spmm: bad tune word 0x%x", tune);
   }
   if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(p, G, V, U, st);

@@ -41,9 +41,21 @@ struct SpmmParams {
   void* Y;
   int64_t ldy;
   int F;
+  // cache policy: 1 = column ids, weights, teleport rows and outputs are touched once per launch ->
+  // streaming (evict-first) loads/stores, so that L2 keeps the gathered feature rows instead
+  int stream;
+  // L2 eviction priority of the gathered feature rows (0 normal, 1 evict-first, 2 evict-last):
+  // pol_hot for column ids tagged hot (bit 31 set by rgbmp_col_tag), pol_cold for the rest.  With
+  // an untagged graph every row takes pol_cold.
+  int pol_hot, pol_cold;
   // epilogue
   rgbmp_epilogue_t ep;
 };
+
+template <typename S>
+__device__ __forceinline__ S ld_stream(const S* q, int stream) {
+  return stream ? __ldcs(q) : __ldg(q);
+}
 
 // ------------------------------------------------------------------------------------------
 // vector load / store helpers.  EPV = elements per 16-byte vector (4 fp32, 8 bf16) or 1 (scalar).
@@ -57,8 +69,15 @@ struct Raw<float, 4> {
   __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void unpack(float (&f)[4]) const { f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w; }
   __device__ __forceinline__ float2 pair(int i) const { return i == 0 ? make_float2(r.x, r.y) : make_float2(r.z, r.w); }
-  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4], int stream = 0) {
+    const float4 v = make_float4(f[0], f[1], f[2], f[3]);
+    if (stream) __stcs(reinterpret_cast<float4*>(p), v);
+    else *reinterpret_cast<float4*>(p) = v;
+  }
+  __device__ __forceinline__ void load_stream(const float* p) { r = __ldcs(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void load_hint(const float* p, uint64_t pol) {
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
   }
 };
 template <>
@@ -68,7 +87,11 @@ struct Raw<float, 1> {
   __device__ __forceinline__ void zero() { r = 0.f; }
   __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = r; }
   __device__ __forceinline__ float2 pair(int) const { return make_float2(r, 0.f); }
-  static __device__ __forceinline__ void store(float* p, const float (&f)[1]) { *p = f[0]; }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[1], int = 0) { *p = f[0]; }
+  __device__ __forceinline__ void load_stream(const float* p) { r = __ldcs(p); }
+  __device__ __forceinline__ void load_hint(const float* p, uint64_t pol) {
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  }
 };
 template <>
 struct Raw<__nv_bfloat16, 8> {
@@ -87,14 +110,21 @@ struct Raw<__nv_bfloat16, 8> {
     const uint32_t w = i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+  __device__ __forceinline__ void load_stream(const __nv_bfloat16* p) { r = __ldcs(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load_hint(const __nv_bfloat16* p, uint64_t pol) {
+    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8], int stream = 0) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+    if (stream) __stcs(reinterpret_cast<uint4*>(p), v);
+    else *reinterpret_cast<uint4*>(p) = v;
   }
 };
 template <>
@@ -104,7 +134,9 @@ struct Raw<__nv_bfloat16, 1> {
   __device__ __forceinline__ void zero() { r = __float2bfloat16(0.f); }
   __device__ __forceinline__ void unpack(float (&f)[1]) const { f[0] = __bfloat162float(r); }
   __device__ __forceinline__ float2 pair(int) const { return make_float2(__bfloat162float(r), 0.f); }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[1]) { *p = __float2bfloat16(f[0]); }
+  __device__ __forceinline__ void load_stream(const __nv_bfloat16* p) { r = *p; }
+  __device__ __forceinline__ void load_hint(const __nv_bfloat16* p, uint64_t) { r = *p; }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[1], int = 0) { *p = __float2bfloat16(f[0]); }
 };
 
 __device__ __forceinline__ float to_f(float x) { return x; }
@@ -160,6 +192,22 @@ __device__ __forceinline__ const char* row_addr(const char* base, uint32_t c, ui
 
 constexpr unsigned FULL = 0xffffffffu;
 
+__device__ __forceinline__ uint64_t make_policy(int kind) {
+  uint64_t pol;
+  if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// gather one 16-byte vector of feature row `ctag & 0x7fffffff`; bit 31 of the id selects the policy
+template <typename T, int EPV>
+__device__ __forceinline__ void gather_vec(Raw<T, EPV>& raw, const char* base, uint32_t ctag, uint32_t row_bytes,
+                                           uint64_t pol_hot, uint64_t pol_cold) {
+  const uint64_t pol = (ctag & 0x80000000u) ? pol_hot : pol_cold;
+  raw.load_hint(reinterpret_cast<const T*>(row_addr(base, ctag & 0x7fffffffu, row_bytes)), pol);
+}
+
 // The loop is WARP-uniform: every lane of the warp runs the same number of batches (the maximum
 // over the warp's groups; with the degree-sorted row schedule the groups of a warp have equal
 // lengths, so nothing is wasted), which lets all shuffles use the full mask (no convergence
@@ -175,22 +223,23 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
                                                  int gl, float2 (&acc)[V][(EPV + 1) / 2]) {
   constexpr int UE = (U < G) ? U : G;   // edges per inner step (a batch holds G ids)
   const uint32_t row_bytes = (uint32_t)(p.ldx * (int64_t)sizeof(T));
+  const uint64_t pol_hot = make_policy(p.pol_hot), pol_cold = make_policy(p.pol_cold);
   const int32_t* __restrict__ col = p.col + k0;
   const float* __restrict__ val = HASW ? p.val + k0 : nullptr;
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;          // <= chunk / long sub-range, fits int
   const int maxlen = __reduce_max_sync(FULL, len);
   if (maxlen == 0) return;
-  int32_t cl = (gl < len) ? __ldg(col + gl) : 0;
+  int32_t cl = (gl < len) ? ld_stream(col + gl, p.stream) : 0;
   float wl = 0.f;
-  if constexpr (HASW) wl = (gl < len) ? __ldg(val + gl) : 0.f;
+  if constexpr (HASW) wl = (gl < len) ? ld_stream(val + gl, p.stream) : 0.f;
   for (int off = 0; off < maxlen; off += G) {
     int nb = len - off;
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
     int32_t cn = 0;
     float wn = 0.f;
     if (off + G + gl < len) {                       // prefetch the next batch of ids / weights
-      cn = __ldg(col + off + G + gl);
-      if constexpr (HASW) wn = __ldg(val + off + G + gl);
+      cn = ld_stream(col + off + G + gl, p.stream);
+      if constexpr (HASW) wn = ld_stream(val + off + G + gl, p.stream);
     }
     if (__all_sync(FULL, nb == G)) {                // every group has a full batch: no predicates
       if constexpr (PIPE && (G / UE) >= 2) {
@@ -199,7 +248,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
         for (int u = 0; u < UE; ++u) {
           const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, u, G);
 #pragma unroll
-          for (int v = 0; v < V; ++v) cur[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+          for (int v = 0; v < V; ++v) gather_vec<T, EPV>(cur[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
         }
 #pragma unroll 1
         for (int j = 0; j < G; j += UE) {
@@ -209,7 +258,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
           for (int u = 0; u < UE; ++u) {
             const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, jn + u, G);
 #pragma unroll
-            for (int v = 0; v < V; ++v) nxt[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(nxt[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
           }
 #pragma unroll
           for (int u = 0; u < UE; ++u) {
@@ -231,7 +280,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
           for (int u = 0; u < UE; ++u) {
             const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);
 #pragma unroll
-            for (int v = 0; v < V; ++v) raw[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(raw[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
           }
 #pragma unroll
           for (int u = 0; u < UE; ++u) {
@@ -252,7 +301,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
           const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);   // lanes past nb hold id 0: a valid row
           if (j + u < nb) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) raw[u][v].load(reinterpret_cast<const T*>(row_addr(xb[v], c, row_bytes)));
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(raw[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
           }
         }
 #pragma unroll
@@ -285,7 +334,8 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
   float t[EPV];
   if (ep.T) {
     Raw<T, EPV> tr;
-    tr.load(reinterpret_cast<const T*>(ep.T) + row * ep.ldt + f);
+    if (p.stream) tr.load_stream(reinterpret_cast<const T*>(ep.T) + row * ep.ldt + f);
+    else tr.load(reinterpret_cast<const T*>(ep.T) + row * ep.ldt + f);
     tr.unpack(t);
   }
 #pragma unroll
@@ -298,13 +348,13 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
     if (reset && ep.reset_when == 2) v = rv[i];
     s[i] = v;
   }
-  if (p.Y) Raw<T, EPV>::store(reinterpret_cast<T*>(p.Y) + row * p.ldy + f, s);
+  if (p.Y) Raw<T, EPV>::store(reinterpret_cast<T*>(p.Y) + row * p.ldy + f, s, p.stream);
   if (ep.Y2) {
     const float s2 = __ldg(ep.out2_scale + row);
     float o[EPV];
 #pragma unroll
     for (int i = 0; i < EPV; ++i) o[i] = __fmul_rn(s2, s[i]);
-    Raw<T, EPV>::store(reinterpret_cast<T*>(ep.Y2) + row * ep.ldy2 + f, o);
+    Raw<T, EPV>::store(reinterpret_cast<T*>(ep.Y2) + row * ep.ldy2 + f, o, p.stream);
   }
 }
 
@@ -460,12 +510,12 @@ int dispatch_w(const SpmmParams& p, cudaStream_t st) {
   return p.val ? launch_cfg<T, EPV, G, V, U, true, PIPE>(p, st) : launch_cfg<T, EPV, G, V, U, false, PIPE>(p, st);
 }
 
-// U field of the tune word: 2 / 4 / 8 = edges per step; +16 = software-pipelined main loop
+// U field of the tune word: 2 / 4 = edges per step; +16 = software-pipelined main loop
+// (V >= 3 and U = 8 never won a sweep on B200 and are no longer instantiated)
 template <typename T, int EPV, int G, int V>
 int dispatch_u(const SpmmParams& p, int U, cudaStream_t st) {
   switch (U) {
     case 2: return dispatch_w<T, EPV, G, V, 2, false>(p, st);
-    case 8: return dispatch_w<T, EPV, G, V, 8, false>(p, st);
     case 18: return dispatch_w<T, EPV, G, V, 2, true>(p, st);
     case 20: return dispatch_w<T, EPV, G, V, 4, true>(p, st);
     default: return dispatch_w<T, EPV, G, V, 4, false>(p, st);
@@ -476,9 +526,7 @@ template <typename T, int EPV, int G>
 int dispatch_v(const SpmmParams& p, int V, int U, cudaStream_t st) {
   switch (V) {
     case 1: return dispatch_u<T, EPV, G, 1>(p, U, st);
-    case 2: return dispatch_u<T, EPV, G, 2>(p, U, st);
-    case 3: return dispatch_u<T, EPV, G, 3>(p, U, st);
-    default: return dispatch_u<T, EPV, G, 4>(p, U, st);
+    default: return dispatch_u<T, EPV, G, 2>(p, U, st);
   }
 }
 

@@ -23,7 +23,9 @@ NORM_INV_SQRT, NORM_INV_MEAN, NORM_COUNT = 0, 1, 2
 
 DEFAULT_CHUNK = 1024        # rows with more edges than this are split ...
 DEFAULT_LONG_CHUNK = 4096   # ... into CTA work items of this many edges
-DEFAULT_WINDOW = 16384      # rows are degree-sorted inside windows of this many rows (0 = natural order)
+HOT_L2_BYTES = 64 << 20     # L2 budget for the hot (most gathered) feature rows; 0 turns the tagging off
+DEFAULT_WINDOW = -1         # row schedule: -1 = global degree sort (fastest on B200, profiles/r01_sweep_v2.txt),
+                            # w > 0 = degree-sorted inside windows of w rows, 0 = natural order
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -55,16 +57,53 @@ class CSR:
         self._split_long_rows()
         self.row_order = None
         window = DEFAULT_WINDOW if window is None else int(window)
+        if window < 0:
+            window = n_rows
         if window > 0 and n_rows > 1 and nnz > 0:
             self.row_order = torch.empty(n_rows, dtype=torch.int32, device=dev)
             ws = _ws(L.rgbmp_row_order_workspace_bytes(n_rows), dev)
             check(L.rgbmp_row_order(ptr(self.rowptr), n_rows, window, ptr(self.row_order), ptr(ws), ws.numel(),
                                     dev.index, st), "row_order")
         self._norm = {}
-        self.struct = GraphStruct(n_rows, n_cols, nnz, ptr(self.rowptr), ptr(self.col), self.chunk, self.long_chunk,
-                                  self.n_long, self.n_items, ptr(self.long_rows), ptr(self.long_item_ptr),
-                                  ptr(self.item_long), ptr(self.item_start), ptr(self.row_order))
+        self._tagged = {}
+        self.struct = self._make_struct(self.col, 0)
         self.ref = C.byref(self.struct)
+
+    def _make_struct(self, col: torch.Tensor, tagged: int) -> GraphStruct:
+        return GraphStruct(self.n_rows, self.n_cols, self.nnz, ptr(self.rowptr), ptr(col), self.chunk, self.long_chunk,
+                           self.n_long, self.n_items, ptr(self.long_rows), ptr(self.long_item_ptr),
+                           ptr(self.item_long), ptr(self.item_start), ptr(self.row_order), tagged)
+
+    def col_freq(self) -> torch.Tensor:
+        """int32 [n_cols]: how often each column (feature row) is gathered by one pass over this CSR."""
+        v = self._norm.get("freq")
+        if v is None:
+            v = torch.empty(max(self.n_cols, 1), dtype=torch.int32, device=self.device)
+            check(lib().rgbmp_col_freq(ptr(self.col), self.nnz, self.n_cols, ptr(v), self.device.index,
+                                       stream_of(self.device)), "col_freq")
+            self._norm["freq"] = v
+        return v
+
+    def hot_ref(self, row_bytes: int):
+        """Descriptor whose column ids carry the hot tag (bit 31) for feature rows of `row_bytes`
+        bytes, or the plain descriptor when the whole feature matrix fits the L2 budget anyway.
+        The hot set = the most frequently gathered rows that fit HOT_L2_BYTES; built once per
+        row size class and cached."""
+        if HOT_L2_BYTES <= 0 or self.nnz == 0 or self.n_cols * row_bytes <= HOT_L2_BYTES:
+            return self.ref
+        k_hot = max(1, HOT_L2_BYTES // max(row_bytes, 1))
+        hit = self._tagged.get(k_hot)
+        if hit is None:
+            freq = self.col_freq()[: self.n_cols]
+            # threshold = frequency of the k_hot-th most popular column (ties above the budget stay cold)
+            thresh = int(torch.kthvalue(freq, self.n_cols - k_hot + 1).values.item()) + 1
+            tagged = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            check(lib().rgbmp_col_tag(ptr(self.col), self.nnz, ptr(freq), thresh, ptr(tagged), self.device.index,
+                                      stream_of(self.device)), "col_tag")
+            st = self._make_struct(tagged, 1)
+            hit = (tagged, st, C.byref(st))
+            self._tagged[k_hot] = hit
+        return hit[2]
 
     def _split_long_rows(self):
         L = lib()

@@ -71,9 +71,16 @@ def make_epilogue(*, row_scale=None, row_div=False, a=1.0, b=0.0, T=None, ldt=0,
     return e
 
 
+def _graph_ref(csr, row_bytes: int, hot: bool = True):
+    if hot and hasattr(csr, "hot_ref"):
+        return csr.hot_ref(row_bytes)
+    return csr.ref
+
+
 def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, ep: Optional[Epilogue] = None,
-             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y[i] = epilogue(sum_k val[k] * x[col[k]]).  `keep` holds tensors referenced by `ep`."""
+             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None, hot: bool = True) -> torch.Tensor:
+    """y[i] = epilogue(sum_k val[k] * x[col[k]]).  `keep` holds tensors referenced by `ep`.
+    hot=True lets feature matrices beyond the L2 budget use the hot-tagged column ids (graph.CSR.hot_ref)."""
     xb, ldx = as_rows(x)
     F = x.size(1)
     if x.size(0) < csr.n_cols:
@@ -84,7 +91,7 @@ def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, e
         y, ldy = out, out.stride(0)
     ws = csr.spmm_workspace(F)
     dev = x.device
-    check(lib().rgbmp_spmm(csr.ref, ptr(val), ptr(xb), ldx, ptr(y), ldy, F, dtype_code(x),
+    check(lib().rgbmp_spmm(_graph_ref(csr, ldx * xb.element_size(), hot), ptr(val), ptr(xb), ldx, ptr(y), ldy, F, dtype_code(x),
                            C.byref(ep) if ep is not None else None, tune, ptr(ws),
                            0 if ws is None else ws.numel(), dev.index, stream_of(dev)), "spmm")
     return y
@@ -100,7 +107,7 @@ def row_scale(x: torch.Tensor, scale: torch.Tensor, divide: bool = False) -> tor
 
 
 def khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilogue] = None, keep=(),
-             hops: bool = False, tune: int = 0):
+             hops: bool = False, tune: int = 0, hot: bool = True):
     """K fused hops.  Returns the final iterate, or (final, [K, N, F] hop outputs) when hops=True."""
     xb, ldx = as_rows(x0)
     N, F = x0.shape
@@ -113,7 +120,7 @@ def khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilo
         pong = torch.empty((N, Fp), dtype=dt, device=dev)
     hop_buf = torch.empty((K, N, Fp), dtype=dt, device=dev) if hops else None
     ws = csr.spmm_workspace(F)
-    check(lib().rgbmp_khop(csr.ref, ptr(val), ptr(xb), ldx, ptr(ping), ptr(pong), Fp, ptr(out), ldo,
+    check(lib().rgbmp_khop(_graph_ref(csr, Fp * xb.element_size(), hot), ptr(val), ptr(xb), ldx, ptr(ping), ptr(pong), Fp, ptr(out), ldo,
                            ptr(hop_buf), Fp, N * Fp, F, dtype_code(x0), K,
                            C.byref(ep) if ep is not None else None, tune, ptr(ws),
                            0 if ws is None else ws.numel(), dev.index, stream_of(dev)), "khop")
@@ -443,8 +450,10 @@ class _GAT(torch.autograd.Function):
         rmax = torch.empty((N, H), dtype=torch.float32, device=xp.device)
         rsum = torch.empty((N, H), dtype=torch.float32, device=xp.device)
         dev = xp.device
+        wsb = lib().rgbmp_gat_workspace_bytes(graph.fwd.ref, H, Cc)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         check(lib().rgbmp_gat_forward(graph.fwd.ref, ptr(xb), ldx, ptr(a_s), ptr(a_d), H, Cc, slope, ptr(drop_csr),
-                                      ptr(out), ldo, ptr(rmax), ptr(rsum), None, 0, dev.index, stream_of(dev)),
+                                      ptr(out), ldo, ptr(rmax), ptr(rsum), ptr(ws), wsb, dev.index, stream_of(dev)),
               "gat_forward")
         ctx.graph, ctx.H, ctx.Cc, ctx.slope = graph, H, Cc, slope
         ctx.save_for_backward(xb, a_s, a_d, rmax, rsum, out, drop_csr)
@@ -457,16 +466,16 @@ class _GAT(torch.autograd.Function):
         dev = dout.device
         db, ldd = as_rows(dout)
         N = g.N
-        S = torch.empty((N, H), dtype=torch.float32, device=dev)
-        check(lib().rgbmp_rowdot(ptr(db), ldd, ptr(out), out.stride(0), N, H, Cc, ptr(S), dev.index, stream_of(dev)),
-              "rowdot")
         dxp, lddx = alloc_rows(N, H * Cc, torch.float32, dev)
         da_s = torch.empty((N, H), dtype=torch.float32, device=dev)
         da_d = torch.zeros((N, H), dtype=torch.float32, device=dev)
         tpos = g.tpos() if drop is not None else None
+        wsb = lib().rgbmp_gat_backward_workspace_bytes(g.bwd.ref, N, H, Cc)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         check(lib().rgbmp_gat_backward(g.bwd.ref, ptr(xb), xb.stride(0), ptr(a_s), ptr(a_d), H, Cc, ctx.slope,
-                                       ptr(drop), ptr(tpos), ptr(rmax), ptr(rsum), ptr(S), ptr(db), ldd, ptr(dxp),
-                                       lddx, ptr(da_s), ptr(da_d), dev.index, stream_of(dev)), "gat_backward")
+                                       ptr(drop), ptr(tpos), ptr(rmax), ptr(rsum), ptr(out), out.stride(0), ptr(db), ldd,
+                                       ptr(dxp), lddx, ptr(da_s), ptr(da_d), N, ptr(ws), wsb, dev.index,
+                                       stream_of(dev)), "gat_backward")
         return dxp, da_s, da_d, None, None, None, None, None
 
 
@@ -555,7 +564,7 @@ def appnp_host(graph: Graph, z0_host: torch.Tensor, out_host: torch.Tensor, K: i
         plan = HostAppnpPlan(graph, F)
     dev = graph.device
     z0d, ping, pong, outd = plan.bufs
-    check(lib().rgbmp_appnp_host(graph.fwd.ref, ptr(plan.dinv), z0_host.data_ptr(), out_host.data_ptr(), F, K,
+    check(lib().rgbmp_appnp_host(graph.fwd.hot_ref(plan.ld * 4), ptr(plan.dinv), z0_host.data_ptr(), out_host.data_ptr(), F, K,
                                  float(alpha), ptr(z0d), ptr(ping), ptr(pong), ptr(outd), plan.ld, ptr(plan.ws),
                                  0 if plan.ws is None else plan.ws.numel(), dev.index, stream_of(dev)), "appnp_host")
     return out_host

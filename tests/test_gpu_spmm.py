@@ -94,8 +94,8 @@ def test_every_launch_shape_gives_the_same_answer():
     xd = x.to(DEV)
     outs = []
     for G in (1, 2, 4, 8, 16, 32):
-        for V in (1, 2, 3, 4):
-            for U in (2, 4, 8, 18, 20):
+        for V in (1, 2):
+            for U in (2, 4, 18, 20):
                 y = p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=G | (V << 8) | (U << 16))
                 assert relerr(y, ref) <= TOL, (G, V, U)
                 outs.append(y)
@@ -104,6 +104,10 @@ def test_every_launch_shape_gives_the_same_answer():
     assert int((~short).sum()) > 0
     for y in outs[1:]:
         assert torch.equal(y[short], outs[0][short])
+    # shapes that are no longer instantiated are rejected, not silently replaced
+    for bad in (1 | (3 << 8) | (4 << 16), 8 | (1 << 8) | (8 << 16), 3 | (1 << 8) | (4 << 16)):
+        with pytest.raises(RuntimeError):
+            p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=bad)
 
 
 def test_unaligned_input_takes_the_scalar_path_and_noncontiguous_views_work():
@@ -196,3 +200,54 @@ def test_linearity_and_adjointness_at_arxiv_scale():
     gm = p.Graph(sg.edge_index, n, p.LOOP_REMOVE_THEN_ADD)
     ones = torch.full((n, 8), 2.5, device=DEV)
     assert torch.equal(p.ops.propagate(ones, gm, "mean"), ones)
+
+
+@pytest.mark.parametrize("case", ["loops_dups", "hub", "medium"])
+def test_col_freq_and_hot_tag_bit_exact(case):
+    """rgbmp_col_freq = bincount(col); rgbmp_col_tag sets bit 31 exactly on ids whose frequency
+    reaches the threshold and leaves the low 31 bits untouched."""
+    p = P()
+    ei, n = CASES[case]()
+    g = p.Graph(ei.to(DEV), n, p.LOOP_ADD_REMAINING)
+    csr = g.fwd
+    freq = csr.col_freq()[:n].cpu().long()
+    assert torch.equal(freq, torch.bincount(csr.col.cpu().long(), minlength=n))
+    import rgb_experiment_b200.graph as G_
+    old = G_.HOT_L2_BYTES
+    try:
+        G_.HOT_L2_BYTES = 40 * 64                     # room for 40 rows of 64 bytes
+        ref = csr.hot_ref(64)
+        tagged, st, _ = csr._tagged[40]
+        assert st.col_tagged == 1 and ref is not csr.ref
+        t = tagged.cpu().long() & 0xFFFFFFFF
+        assert torch.equal(t & 0x7FFFFFFF, csr.col.cpu().long())
+        hot = (t >> 31).bool()
+        k = 40
+        thresh = int(torch.sort(freq, descending=True).values[k - 1]) + 1
+        assert torch.equal(hot, freq[csr.col.cpu().long()] >= thresh)
+        assert int((freq >= thresh).sum()) <= k
+    finally:
+        G_.HOT_L2_BYTES = old
+
+
+@pytest.mark.parametrize("case", ["hub", "medium"])
+@pytest.mark.parametrize("F", [7, 47, 100])
+def test_hot_tagged_gathers_do_not_change_results(case, F):
+    """The hot tag only selects an L2 eviction priority: results are bit-identical with and without it."""
+    p = P()
+    import rgb_experiment_b200.graph as G_
+    ei, n = CASES[case]()
+    x = torch.randn(n, F, generator=torch.Generator().manual_seed(F)).to(DEV)
+    g = p.Graph(ei.to(DEV), n, p.LOOP_ADD_REMAINING)
+    val = g.gcn_val(False)
+    plain = p.ops.spmm_raw(g.fwd, x, val, hot=False)
+    old = G_.HOT_L2_BYTES
+    try:
+        G_.HOT_L2_BYTES = 4096
+        tagged = p.ops.spmm_raw(g.fwd, x, val, hot=True)
+        assert len(g.fwd._tagged) == 1
+        k10 = p.ops.appnp(x, g, 3, 0.1)
+    finally:
+        G_.HOT_L2_BYTES = old
+    assert torch.equal(plain, tagged)
+    assert torch.equal(k10, p.ops.appnp(x, g, 3, 0.1))
