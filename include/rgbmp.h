@@ -148,6 +148,7 @@ typedef struct rgbmp_graph {
 } rgbmp_graph_t;
 
 /* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
+ *   s_i = acc_in ? acc_in[i,:] + s_i : s_i                          (column-blocked accumulation)
  *   v = row_scale ? (row_div ? s_i / row_scale[i] : row_scale[i]*s_i) : s_i
  *   if reset_when==1 and reset_mask[i]: v = reset_val[i,:]          (PTA label_propagation,
  *                                                                    itexperiments.py:715-717)
@@ -157,6 +158,7 @@ typedef struct rgbmp_graph {
  *   if reset_when==2 and reset_mask[i]: v = reset_val[i,:]           (C&S autoscale=False)
  *   Y[i,:] = v (if Y) ;  Y2[i,:] = out2_scale[i]*v (if Y2)           (pre-scaled copy for the next hop)
  */
+#define RGBMP_MAX_PEERS 8
 typedef struct rgbmp_epilogue {
   const float*   row_scale;
   int32_t        row_div;      /* 1: divide by row_scale[i] (scatter-mean's true divide) */
@@ -173,6 +175,18 @@ typedef struct rgbmp_epilogue {
   const float*   out2_scale;
   void*          Y2;
   int64_t        ldy2;
+  const void*    acc_in;       /* optional [n_rows, ld_acc], dtype of X: s_i = acc_in[i,:] + s_i before anything
+                                  else (partial sums of the previous column block; may alias Y)             */
+  int64_t        ld_acc;
+  int32_t        skip_empty;   /* 1: rows without edges in this launch are left untouched                   */
+  /* fused all-gather (row-partitioned multi-GPU propagation): the finished row i is also
+   * stored to peer_out[q] + (peer_row0 + i) * ld_peer for q < n_peers -- peer-mapped buffers of the
+   * other GPUs of the NVSwitch box (rgbmp_peer_open), written with plain stores over NVLink while the
+   * kernel is still aggregating other rows.  Same dtype as Y. */
+  void*          peer_out[RGBMP_MAX_PEERS];
+  int32_t        n_peers;
+  int64_t        peer_row0;
+  int64_t        ld_peer;
 } rgbmp_epilogue_t;
 
 /* CSR SpMM  Y[i,:] = epilogue( sum_k val[k] * X[col[k],:] ), k in rowptr[i]..rowptr[i+1].
@@ -208,10 +222,26 @@ int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t
                int F, int dtype, int K, const rgbmp_epilogue_t* ep, int tune,
                void* ws, size_t ws_bytes, int device, void* stream);
 
+/* Device-wide knob (the one call that touches device state): size of the L2 set-aside that
+ * evict-last ("persisting") lines may occupy, clamped to the device maximum; *granted = new limit. */
+int rgbmp_l2_persist(int device, size_t bytes, size_t* granted);
+
 /* Y[i,:] = scale[i] * X[i,:]  (the D^-1/2 pre-scaling of the folded normalisation), or with
  * divide=1  Y[i,:] = X[i,:] / scale[i]  (backward of scatter-mean: grad / count). */
 int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, void* Y, int64_t ldy,
                     int64_t n_rows, int F, int dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b2) peer memory for the row-partitioned multi-GPU path (one process per GPU, NVLink P2P)
+ * ------------------------------------------------------------------------------------------ */
+#define RGBMP_IPC_HANDLE_BYTES 64
+/* Allocate `bytes` of device memory that other processes of the box can map (cudaMalloc +
+ * cudaIpcGetMemHandle).  The one place where the library owns memory: IPC needs a whole allocation. */
+int rgbmp_peer_alloc(size_t bytes, void** ptr, unsigned char handle[RGBMP_IPC_HANDLE_BYTES], int device);
+int rgbmp_peer_free(void* ptr, int device);
+/* Map a peer process's allocation into this process (cudaIpcOpenMemHandle, enables peer access). */
+int rgbmp_peer_open(const unsigned char handle[RGBMP_IPC_HANDLE_BYTES], void** ptr, int device);
+int rgbmp_peer_close(void* ptr, int device);
 
 /* ------------------------------------------------------------------------------------------
  * (c) attention kernels

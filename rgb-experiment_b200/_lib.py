@@ -28,7 +28,8 @@ class Epilogue(C.Structure):
     _fields_ = [("row_scale", c_vp), ("row_div", c_i32), ("reset_mask", c_vp), ("reset_val", c_vp),
                 ("ld_reset", c_i64), ("reset_when", c_i32), ("a", c_f32), ("b", c_f32), ("T", c_vp),
                 ("ldt", c_i64), ("clamp", c_i32), ("lo", c_f32), ("hi", c_f32), ("out2_scale", c_vp),
-                ("Y2", c_vp), ("ldy2", c_i64)]
+                ("Y2", c_vp), ("ldy2", c_i64), ("acc_in", c_vp), ("ld_acc", c_i64), ("skip_empty", c_i32),
+                ("peer_out", c_vp * 8), ("n_peers", c_i32), ("peer_row0", c_i64), ("ld_peer", c_i64)]
 
 
 _lib = None
@@ -78,6 +79,11 @@ def lib():
         "rgbmp_gat_backward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
                                          C.c_int, c_vp]),
+        "rgbmp_peer_alloc": (C.c_int, [c_sz, c_vp, c_vp, C.c_int]),
+        "rgbmp_peer_free": (C.c_int, [c_vp, C.c_int]),
+        "rgbmp_peer_open": (C.c_int, [c_vp, c_vp, C.c_int]),
+        "rgbmp_peer_close": (C.c_int, [c_vp, C.c_int]),
+        "rgbmp_l2_persist": (C.c_int, [C.c_int, c_sz, c_vp]),
         "rgbmp_col_freq": (C.c_int, [c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp]),
         "rgbmp_col_tag": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, C.c_int, c_vp]),
         "rgbmp_rowdot": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),

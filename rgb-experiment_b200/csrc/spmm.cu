@@ -1,4 +1,5 @@
 // CSR SpMM host-side dispatch, K-hop driver, host-buffer entry point (sm_100a).
+#include <string.h>
 #include "spmm_kernels.cuh"
 
 namespace rgbmp {
@@ -93,14 +94,21 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
   if (p.ep.reset_when != 0 && (!p.ep.reset_mask || !p.ep.reset_val))
     return fail(RGBMP_EINVAL, "rgbmp_spmm: reset_when set without reset_mask/reset_val");
   if (p.ep.Y2 && !p.ep.out2_scale) return fail(RGBMP_EINVAL, "rgbmp_spmm: Y2 without out2_scale");
-  if (!Y && !p.ep.Y2) return fail(RGBMP_EINVAL, "rgbmp_spmm: no output");
+  if (!Y && !p.ep.Y2 && p.ep.n_peers <= 0) return fail(RGBMP_EINVAL, "rgbmp_spmm: no output");
+  if (p.ep.n_peers < 0 || p.ep.n_peers > RGBMP_MAX_PEERS) return fail(RGBMP_EINVAL, "rgbmp_spmm: bad n_peers");
+  for (int q = 0; q < p.ep.n_peers; ++q)
+    if (!p.ep.peer_out[q]) return fail(RGBMP_EINVAL, "rgbmp_spmm: null peer buffer %d", q);
 
   const int esz = dtype == RGBMP_BF16 ? 2 : 4;
   const int epv_vec = 16 / esz;
   auto aligned = [&](const void* ptr, int64_t ld) {
     return ptr == nullptr || ((((uintptr_t)ptr) & 15) == 0 && (ld % epv_vec) == 0 && ld >= align_up(F, epv_vec));
   };
-  const bool vec_ok = aligned(X, ldx) && aligned(Y, ldy) && aligned(p.ep.T, p.ep.ldt) && aligned(p.ep.Y2, p.ep.ldy2);
+  const bool vec_ok = aligned(X, ldx) && aligned(Y, ldy) && aligned(p.ep.T, p.ep.ldt) && aligned(p.ep.Y2, p.ep.ldy2) &&
+                      aligned(p.ep.acc_in, p.ep.ld_acc) &&
+                      (p.ep.n_peers == 0 || ((p.ep.ld_peer % epv_vec) == 0 && ((p.ep.peer_row0 * p.ep.ld_peer) % epv_vec) == 0));
+  for (int q = 0; q < p.ep.n_peers; ++q)
+    if ((((uintptr_t)p.ep.peer_out[q]) & 15) != 0) return fail(RGBMP_EALIGN, "rgbmp_spmm: peer buffer %d not 16-byte aligned", q);
   const int epv = vec_ok ? epv_vec : 1;
   if (dtype == RGBMP_BF16 && !vec_ok)
     return fail(RGBMP_EALIGN, "rgbmp_spmm: bf16 needs 16-byte aligned pointers and ld %% 8 == 0");
@@ -212,6 +220,58 @@ int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t
     if (lastp != out)
       RGBMP_CUDA(cudaMemcpy2DAsync(out, ldo * esz, lastp, ld_hops * esz, F * esz, g->n_rows, cudaMemcpyDeviceToDevice, st));
   }
+  return 0;
+}
+
+int rgbmp_peer_alloc(size_t bytes, void** ptr, unsigned char handle[RGBMP_IPC_HANDLE_BYTES], int device) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == RGBMP_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!ptr || !handle || bytes == 0) return fail(RGBMP_EINVAL, "rgbmp_peer_alloc: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_peer_alloc: bad device");
+  void* p = nullptr;
+  RGBMP_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return 0;
+}
+
+int rgbmp_peer_free(void* ptr, int device) {
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_peer_free: bad device");
+  if (ptr) RGBMP_CUDA(cudaFree(ptr));
+  return 0;
+}
+
+int rgbmp_peer_open(const unsigned char handle[RGBMP_IPC_HANDLE_BYTES], void** ptr, int device) {
+  if (!handle || !ptr) return fail(RGBMP_EINVAL, "rgbmp_peer_open: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_peer_open: bad device");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  RGBMP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int rgbmp_peer_close(void* ptr, int device) {
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_peer_close: bad device");
+  if (ptr) RGBMP_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+int rgbmp_l2_persist(int device, size_t bytes, size_t* granted) {
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_l2_persist: bad device");
+  int maxb = 0;
+  RGBMP_CUDA(cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, device));
+  if (bytes > (size_t)maxb) bytes = (size_t)maxb;
+  RGBMP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+  size_t got = 0;
+  RGBMP_CUDA(cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize));
+  if (granted) *granted = got;
   return 0;
 }
 

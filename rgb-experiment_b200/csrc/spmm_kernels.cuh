@@ -200,12 +200,16 @@ __device__ __forceinline__ uint64_t make_policy(int kind) {
   return pol;
 }
 
-// gather one 16-byte vector of feature row `ctag & 0x7fffffff`; bit 31 of the id selects the policy
+// gather one 16-byte vector of feature row `ctag & 0x7fffffff`; bit 31 of the id selects the policy.
+// The L2 policy travels in a memory DESCRIPTOR, which is warp-uniform on sm_100 (ptxas moves a
+// per-lane policy through R2UR, i.e. silently applies one lane's choice to the whole warp), so the
+// choice is expressed as two predicated loads with kernel-uniform policies.
 template <typename T, int EPV>
 __device__ __forceinline__ void gather_vec(Raw<T, EPV>& raw, const char* base, uint32_t ctag, uint32_t row_bytes,
                                            uint64_t pol_hot, uint64_t pol_cold) {
-  const uint64_t pol = (ctag & 0x80000000u) ? pol_hot : pol_cold;
-  raw.load_hint(reinterpret_cast<const T*>(row_addr(base, ctag & 0x7fffffffu, row_bytes)), pol);
+  const T* q = reinterpret_cast<const T*>(row_addr(base, ctag & 0x7fffffffu, row_bytes));
+  if (ctag & 0x80000000u) raw.load_hint(q, pol_hot);
+  else raw.load_hint(q, pol_cold);
 }
 
 // The loop is WARP-uniform: every lane of the warp runs the same number of batches (the maximum
@@ -331,6 +335,14 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
 #pragma unroll
     for (int i = 0; i < EPV; ++i) rv[i] = (f + i < p.F) ? ep.reset_val[row * ep.ld_reset + f + i] : 0.f;
   }
+  if (ep.acc_in) {
+    Raw<T, EPV> ar;
+    float a[EPV];
+    ar.load_stream(reinterpret_cast<const T*>(ep.acc_in) + row * ep.ld_acc + f);
+    ar.unpack(a);
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) s[i] = __fadd_rn(a[i], s[i]);
+  }
   float t[EPV];
   if (ep.T) {
     Raw<T, EPV> tr;
@@ -349,6 +361,8 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
     s[i] = v;
   }
   if (p.Y) Raw<T, EPV>::store(reinterpret_cast<T*>(p.Y) + row * p.ldy + f, s, p.stream);
+  for (int q = 0; q < ep.n_peers; ++q)   // fused all-gather: push the finished row to every peer over NVLink
+    Raw<T, EPV>::store(reinterpret_cast<T*>(ep.peer_out[q]) + (ep.peer_row0 + row) * ep.ld_peer + f, s, 0);
   if (ep.Y2) {
     const float s2 = __ldg(ep.out2_scale + row);
     float o[EPV];
@@ -397,7 +411,7 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_rows_kernel(const SpmmParam
 #pragma unroll
     for (int i = 0; i < (EPV + 1) / 2; ++i) acc[v][i] = make_float2(0.f, 0.f);
   accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, gl, acc);
-  if (row < 0) return;
+  if (row < 0 || (p.ep.skip_empty && k1 == k0)) return;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     if (active[v]) {

@@ -60,7 +60,8 @@ def alloc_rows(N: int, F: int, dtype, device) -> Tuple[torch.Tensor, int]:
 
 def make_epilogue(*, row_scale=None, row_div=False, a=1.0, b=0.0, T=None, ldt=0, clamp=None,
                   reset_mask=None, reset_val=None, ld_reset=0, reset_when=RESET_NONE,
-                  out2_scale=None) -> Epilogue:
+                  out2_scale=None, acc_in=None, ld_acc=0, skip_empty=False, peers=(), peer_row0=0,
+                  ld_peer=0) -> Epilogue:
     e = Epilogue()
     e.row_scale, e.row_div = ptr(row_scale), int(bool(row_div))
     e.reset_mask, e.reset_val, e.ld_reset, e.reset_when = ptr(reset_mask), ptr(reset_val), ld_reset, reset_when
@@ -68,6 +69,12 @@ def make_epilogue(*, row_scale=None, row_div=False, a=1.0, b=0.0, T=None, ldt=0,
     if clamp is not None:
         e.clamp, e.lo, e.hi = 1, float(clamp[0]), float(clamp[1])
     e.out2_scale = ptr(out2_scale)
+    e.acc_in, e.ld_acc, e.skip_empty = ptr(acc_in), ld_acc, int(bool(skip_empty))
+    if len(peers) > 8:
+        raise RuntimeError("at most 8 peer buffers (one NVSwitch box)")
+    for q, pp in enumerate(peers):          # raw device pointers (ints) of peer-mapped buffers
+        e.peer_out[q] = int(pp)
+    e.n_peers, e.peer_row0, e.ld_peer = len(peers), int(peer_row0), int(ld_peer)
     return e
 
 
@@ -78,14 +85,17 @@ def _graph_ref(csr, row_bytes: int, hot: bool = True):
 
 
 def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, ep: Optional[Epilogue] = None,
-             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None, hot: bool = True) -> torch.Tensor:
+             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None, hot: bool = True,
+             store_local: bool = True) -> Optional[torch.Tensor]:
     """y[i] = epilogue(sum_k val[k] * x[col[k]]).  `keep` holds tensors referenced by `ep`.
     hot=True lets feature matrices beyond the L2 budget use the hot-tagged column ids (graph.CSR.hot_ref)."""
     xb, ldx = as_rows(x)
     F = x.size(1)
     if x.size(0) < csr.n_cols:
         raise RuntimeError(f"x has {x.size(0)} rows but the graph addresses {csr.n_cols}")
-    if out is None:
+    if not store_local:                       # every store goes through ep.peer_out / ep.Y2
+        y, ldy = None, 0
+    elif out is None:
         y, ldy = alloc_rows(csr.n_rows, F, x.dtype, x.device)
     else:
         y, ldy = out, out.stride(0)

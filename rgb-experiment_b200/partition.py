@@ -111,16 +111,87 @@ class LocalBlock:
               "gcn_edge_weight")
 
 
-class PartitionedAPPNP:
-    """APPNP / LP-style K-hop propagation over a LocalBlock; per hop: NCCL all-gather of the
-    iterate rows, then the fused SpMM (+teleport epilogue) on the local rows."""
+class PeerBuffers:
+    """`n_buf` device buffers of [rows, ld] elements per rank, each mapped into every other rank of
+    the box through CUDA IPC (rgbmp_peer_alloc / rgbmp_peer_open), so that a kernel on rank p can
+    store straight into rank q's copy over NVLink.  ptrs[b][q] = address (in THIS process) of rank
+    q's buffer b; local[b] = this rank's buffer b as a torch tensor."""
 
-    def __init__(self, block: LocalBlock, F: int, group=None):
+    def __init__(self, rows: int, ld: int, dtype, device, rank: int, world: int, group=None, n_buf: int = 2):
+        import ctypes as C
+        from ._lib import check, lib
+        L = lib()
+        self.device, self.rank, self.world, self._open, self._own = device, rank, world, [], []
+        esz = torch.empty((), dtype=dtype).element_size()
+        nbytes = rows * ld * esz
+        handles = []
+        for _ in range(n_buf):
+            p, h = C.c_void_p(), (C.c_ubyte * 64)()
+            check(L.rgbmp_peer_alloc(nbytes, C.byref(p), h, device.index), "peer_alloc")
+            self._own.append(p.value)
+            handles.append(bytes(h))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.ptrs = []
+        for b in range(n_buf):
+            row = []
+            for q in range(world):
+                if q == rank:
+                    row.append(self._own[b])
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(gathered[q][b])
+                    check(L.rgbmp_peer_open(hb, C.byref(p), device.index), "peer_open")
+                    self._open.append(p.value)
+                    row.append(p.value)
+            self.ptrs.append(row)
+        self.local = [_wrap(p, nbytes, device).view(dtype).view(rows, ld) for p in self._own]
+
+    def close(self):
+        from ._lib import lib
+        L = lib()
+        torch.cuda.synchronize(self.device)
+        for p in self._open:
+            L.rgbmp_peer_close(p, self.device.index)
+        self._open = []
+        self.local = []
+        for p in self._own:
+            L.rgbmp_peer_free(p, self.device.index)
+        self._own = []
+
+
+class _RawCuda:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _wrap(ptr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+class PartitionedAPPNP:
+    """APPNP / LP-style K-hop propagation over a LocalBlock.
+
+    mode="push" (default on a multi-GPU box): ONE fused kernel per hop -- the SpMM's epilogue
+    stores every finished row of the new iterate into ALL ranks' copies of the full iterate over
+    NVLink (peer-mapped buffers, ping/pong), so the all-gather overlaps the aggregation row by row;
+    a 4-byte NCCL all-reduce orders the hops.
+    mode="allgather": the baseline -- NCCL all_gather_into_tensor of the iterate rows, then the SpMM."""
+
+    def __init__(self, block: LocalBlock, F: int, group=None, mode: str = "push", dtype=torch.float32):
         from . import ops
-        self.block, self.F, self.group = block, F, group
-        self.ld = ops.padded_width(F)
+        self.block, self.F, self.group, self.dtype = block, F, group, dtype
+        self.ld = ops.padded_width(F, dtype)
         dev = block.csr.device
         R, P = block.R, block.world
+        self.mode = mode if P > 1 else "allgather"
+        self.launches_per_hop = 1 + (2 if block.csr.n_items > 0 else 0)
+        if self.mode == "push":
+            self.peers = PeerBuffers(R * P, self.ld, dtype, dev, block.rank, P, group, n_buf=2)
+            self.tick = torch.zeros(1, dtype=torch.int32, device=dev)
+            for t in self.peers.local:
+                t.zero_()
+            return
         self.full = torch.empty((R * P, self.ld), dtype=torch.float32, device=dev)
         self.ping = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
         self.pong = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
@@ -138,4 +209,20 @@ class PartitionedAPPNP:
 
     def run(self, z0_local: torch.Tensor, K: int, alpha: float) -> torch.Tensor:
         """z0_local: [R, ld] (padded rows beyond N are zero).  Returns this rank's rows of z_K."""
-        return self.driver.run(z0_local, K, 1.0 - alpha, alpha, self.full)
+        if self.mode != "push":
+            return self.driver.run(z0_local, K, 1.0 - alpha, alpha, self.full)
+        from . import ops
+        blk, F, R = self.block, self.F, self.block.R
+        full = self.peers.local
+        dist.all_gather_into_tensor(full[0], z0_local, group=self.group)          # iterate 0 everywhere
+        for k in range(K):
+            src, nxt = full[k & 1], (k + 1) & 1
+            ep = ops.make_epilogue(a=1.0 - alpha, b=alpha, T=z0_local, ldt=z0_local.stride(0),
+                                   peers=self.peers.ptrs[nxt], peer_row0=blk.rank * R, ld_peer=self.ld)
+            ops.spmm_raw(blk.csr, src[:, :F], blk.val, ep=ep, keep=(z0_local,), store_local=False)
+            dist.all_reduce(self.tick, group=self.group)     # orders the hops: every push has landed
+        return full[K & 1][blk.rank * R:(blk.rank + 1) * R]
+
+    def close(self):
+        if self.mode == "push":
+            self.peers.close()

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Multi-GPU parity + timing of the row-partitioned K-hop propagation (run under torchrun, one rank
+per GPU):  push mode (SpMM epilogue stores into every peer over NVLink) and all-gather mode (NCCL)
+must both equal the single-GPU result bit for bit.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/mgpu_check.py [--workload products] [--steps 5]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="medium")
+    ap.add_argument("--F", type=int, default=47)
+    ap.add_argument("--K", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
+    args = ap.parse_args()
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    import rgb_experiment_b200 as P
+    import rgb_experiment_b200.partition as PT
+    import rgb_experiment_b200.synth as S
+    if args.workload == "medium":
+        sg = S.make_graph(300_001, 6_000_000, 8, 4, device=dev, features=False)
+    else:
+        sg = S.make_named(args.workload, device=dev, features=False)
+    N, F, K, alpha = sg.num_nodes, args.F, args.K, 0.1
+    blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, rank, world)
+    R = blk.R
+    z0 = torch.randn(N, F, device=dev, generator=torch.Generator(device=dev).manual_seed(1))   # same on every rank
+    res = {}
+    for mode in ("allgather", "push"):
+        prop = PT.PartitionedAPPNP(blk, F, mode=mode)
+        z0l = torch.zeros((R, prop.ld), device=dev)
+        z0l[: blk.hi - blk.lo, :F] = z0[blk.lo:blk.hi]
+        out = prop.run(z0l, K, alpha).clone()
+        for _ in range(2):
+            prop.run(z0l, K, alpha)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            prop.run(z0l, K, alpha)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        full = torch.empty((R * world, prop.ld), device=dev)
+        dist.all_gather_into_tensor(full, out.contiguous())
+        res[mode] = (full[:N, :F].clone(), float(t.item()))
+        prop.close()
+        del prop
+    ok = {}
+    if rank == 0:
+        g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
+        ref = P.ops.appnp(z0, g, K, alpha)
+        for mode, (y, ms) in res.items():
+            ok[mode] = bool(torch.equal(y, ref))
+        line = {"workload": args.workload, "N": N, "nnz": blk.nnz_global, "F": F, "K": K, "world": world,
+                "bit_equal_to_single_gpu": ok,
+                "ms_per_step": {m: round(v[1], 3) for m, v in res.items()},
+                "gteps": {m: round(blk.nnz_global * K / v[1] / 1e6, 2) for m, v in res.items()}}
+        print(json.dumps(line), flush=True)
+    flag = torch.tensor([1 if (rank != 0 or all(ok.values())) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,12 +39,20 @@ def main():
     ap.add_argument("--policies", default="default", help="comma list: default | off (untagged) | hHcC with H,C in 0..2 "
                     "(L2 priority of hot / cold gathered rows: 0 normal, 1 evict-first, 2 evict-last)")
     ap.add_argument("--hot-mb", default="64", help="comma list of L2 budgets (MB) for the hot rows")
+    ap.add_argument("--persist-mb", type=int, default=-1, help="set the persisting-L2 set-aside (MB) first")
     ap.add_argument("--shapes", default="", help="only these G:V:U shapes, e.g. 8:2:18,16:1:20")
     args = ap.parse_args()
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.synth as S
     from rgb_experiment_b200 import graph as G_
     dev = torch.device("cuda:0")
+    if args.persist_mb >= 0:
+        import ctypes
+        from rgb_experiment_b200._lib import lib, check
+        got = ctypes.c_size_t(0)
+        torch.zeros(1, device=dev)
+        check(lib().rgbmp_l2_persist(0, args.persist_mb << 20, ctypes.addressof(got)), "l2_persist")
+        print(json.dumps({"persisting_l2_bytes": got.value}), flush=True)
     plans = {"products": [(47, torch.float32), (100, torch.float32)],
              "arxiv": [(256, torch.float32), (40, torch.float32), (128, torch.bfloat16)],
              "reddit": [(64, torch.float32), (41, torch.float32)]}
