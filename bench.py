@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--fold", type=int, default=1,
                     help="1 (default): D^-1/2 (A+I) D^-1/2 applied as row scalings around an unweighted sum (no per-edge "
                          "weight stream); 0: per-edge gcn_norm weights exactly as PyG multiplies them")
+    ap.add_argument("--feature-groups", type=int, default=0,
+                    help="N>1: Pf of the Pr x Pf process grid (features split Pf ways, rows N/Pf ways); 0 = auto")
     ap.add_argument("--exchange", default="push", choices=["push", "allgather"],
                     help="N>1: fused push of finished rows into every peer over NVLink (default) or NCCL all-gather")
     args = ap.parse_args()
@@ -200,14 +202,18 @@ def main():
 
         launches_per_step = K_HOPS * (1 + (2 if n_items > 0 else 0)) + (1 if args.fold else 0)
     else:
-        blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, rank, world)
+        Pf = args.feature_groups if args.feature_groups > 0 else PT.auto_feature_groups(world, F)
+        grid = PT.Grid(rank, world, Pf)
+        blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group)
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
         nnz = blk.nnz_global
-        prop = PT.PartitionedAPPNP(blk, F, mode=args.exchange)
+        flo, fhi = grid.feature_slice(F)
+        F_local = fhi - flo
+        prop = PT.PartitionedAPPNP(blk, F_local, group=grid.row_group, mode=args.exchange)
         z0l = torch.zeros((blk.R, prop.ld), device=dev)
-        z0l[: blk.hi - blk.lo, :F] = torch.randn(blk.hi - blk.lo, F, device=dev,
-                                                 generator=torch.Generator(device=dev).manual_seed(1 + rank))
+        z0l[: blk.hi - blk.lo, :F_local] = torch.randn(blk.hi - blk.lo, F_local, device=dev,
+                                                       generator=torch.Generator(device=dev).manual_seed(1 + rank))
 
         def step():
             return prop.run(z0l, K_HOPS, ALPHA)
@@ -282,7 +288,10 @@ def main():
 
     peak, peak_kind = peaks()
     weighted = (world > 1) or not args.fold            # the partitioned path streams per-edge weights
-    hop_bytes = algorithmic_bytes_per_hop(nnz // world, N // world, F, weighted=weighted)
+    if world > 1:                                      # per GPU: nnz/Pr edges of F/Pf-wide rows
+        hop_bytes = algorithmic_bytes_per_hop(nnz // grid.Pr, N // grid.Pr, F_local, weighted=weighted)
+    else:
+        hop_bytes = algorithmic_bytes_per_hop(nnz, N, F, weighted=weighted)
     hop_ms = ms_per_step / K_HOPS
     achieved = hop_bytes / (hop_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -320,7 +329,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"APPNP K={K_HOPS} alpha={ALPHA} propagate, ogbn-products-shaped R-MAT graph "
                                    f"(N={N}, E={nnz - N} directed + {N} self loops, F={F} fp32)",
-                       "hops_per_step": K_HOPS, "nnz": nnz, "parallelism": f"row-partition x{world}, exchange={args.exchange}" if world > 1 else "single",
+                       "hops_per_step": K_HOPS, "nnz": nnz, "parallelism": (f"{grid.Pr} row blocks x {grid.Pf} feature slices, exchange={args.exchange}"
+                                       if world > 1 else "single"),
                        "l2": "inputs larger than L2 (features 470 MB, col 505 MB vs 126 MB L2)",
                        "norm": "per-edge weights" if weighted else "folded row scaling (same operator, no per-edge weight stream)", "graph_build_ms": build_ms},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,

@@ -51,6 +51,28 @@ class CSR:
         check(L.rgbmp_csr_build(ptr(key), ptr(other), nnz, n_rows, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
                                 ptr(ws), ws.numel(), dev.index, st), "csr_build")
         self.col, self.eid = self.col[:nnz], self.eid[:nnz]
+        self._finish(chunk, long_chunk, window)
+
+    @classmethod
+    def from_arrays(cls, rowptr: torch.Tensor, col: torch.Tensor, n_cols: int, chunk: int = DEFAULT_CHUNK,
+                    long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None) -> "CSR":
+        """Wrap a CSR that exists already (row-generated graphs, synth.rowgen_block): rowptr int64
+        [n_rows+1], col int32 [nnz] on the device.  No edge ids (eid is None)."""
+        _lib.require_cuda(rowptr, "rowptr")
+        if rowptr.dtype != torch.int64 or col.dtype != torch.int32:
+            raise RuntimeError("CSR.from_arrays needs int64 rowptr and int32 col")
+        self = cls.__new__(cls)
+        self.n_rows, self.n_cols, self.nnz, self.device = rowptr.numel() - 1, int(n_cols), col.numel(), rowptr.device
+        if self.nnz >= (1 << 31):
+            raise RuntimeError("nnz >= 2^31 in one partition: use more row blocks")
+        self.rowptr, self.col, self.eid = rowptr.contiguous(), col.contiguous(), None
+        self._finish(chunk, long_chunk, window)
+        return self
+
+    def _finish(self, chunk: int, long_chunk: int, window: Optional[int]):
+        L = lib()
+        dev, n_rows, nnz = self.device, self.n_rows, self.nnz
+        st = stream_of(dev)
         self.chunk, self.long_chunk = int(chunk), int(long_chunk)
         self.n_long = self.n_items = 0
         self.long_rows = self.long_item_ptr = self.item_long = self.item_start = None

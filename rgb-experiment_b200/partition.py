@@ -25,6 +25,50 @@ def row_range(N: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(N, lo + R)
 
 
+class Grid:
+    """Process grid of a K-hop propagation: `Pr` row groups x `Pf` feature groups (world = Pr * Pf).
+
+    K-hop propagation acts on every feature column independently, so the feature axis can be
+    split with NO communication; only ranks that share a feature slice (a "row group" of Pr ranks)
+    exchange iterate rows.  Against the pure row partition (Pf = 1) a grid divides the per-hop
+    NVLink volume of every GPU by Pf -- (Pr-1)/Pr * N * F/Pf elements instead of (P-1)/P * N * F --
+    at the same gather bytes per GPU (P/Pf times fewer rows... of F/Pf-wide features over Pf times more edges).
+    rank = rp * Pf + fp."""
+
+    def __init__(self, rank: int, world: int, feature_groups: int = 1):
+        if world % feature_groups != 0:
+            raise RuntimeError(f"feature_groups={feature_groups} does not divide world={world}")
+        self.rank, self.world, self.Pf, self.Pr = rank, world, feature_groups, world // feature_groups
+        self.rp, self.fp = rank // feature_groups, rank % feature_groups
+        self.row_group = None          # torch.distributed group of the ranks sharing my feature slice
+        if world > 1 and feature_groups > 1:
+            for f in range(feature_groups):   # every rank creates every group, in the same order
+                g = dist.new_group([r * feature_groups + f for r in range(self.Pr)])
+                if f == self.fp:
+                    self.row_group = g
+
+    def feature_slice(self, F: int, align: int = 4, fp: Optional[int] = None):
+        """[lo, hi) of the feature columns of feature group `fp` (default: mine).  Slices start on
+        `align`-element boundaries (16-byte vectors) and the vector units are spread evenly."""
+        fp = self.fp if fp is None else fp
+        units = (F + align - 1) // align
+        base, rem = divmod(units, self.Pf)
+        if base == 0:
+            raise RuntimeError(f"feature_groups={self.Pf} exceeds the {units} {align}-element vectors of F={F}")
+        lo_u = fp * base + min(fp, rem)
+        hi_u = lo_u + base + (1 if fp < rem else 0)
+        return min(F, lo_u * align), min(F, hi_u * align)
+
+
+def auto_feature_groups(world: int, F: int) -> int:
+    """Feature groups of the default grid.  The per-hop NVLink volume of a GPU shrinks with Pf while
+    rows get narrower (F/Pf); measured on 8 B200s with the products-shaped APPNP (F=47), see
+    profiles/r01_multigpu.txt."""
+    if world >= 8 and F >= 32:
+        return 2
+    return 1
+
+
 def local_edges(e_src: torch.Tensor, e_dst: torch.Tensor, lo: int, hi: int):
     """Edges whose TARGET falls in [lo, hi), order preserved: (local target id, global source id).
     Because the filter keeps the relative order, the stable CSR of the bucket equals the matching
@@ -98,7 +142,34 @@ class LocalBlock:
         key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
         del e_src, e_dst
         self.csr = CSR(key, other, self.R, self.R * world)
-        self.nnz_local = key.numel()
+        self._norms(group)
+
+    @classmethod
+    def from_rowgen(cls, n_nodes: int, n_edges: int, rank: int, world: int, group=None, device=None, **gen_kw):
+        """Row block of a row-generated graph (synth.rowgen_block): the CSR exists by construction --
+        no edge list, no sort -- and each rank generates only its own rows (config C5)."""
+        from . import synth
+        from .graph import CSR
+        self = cls.__new__(cls)
+        self.N, self.rank, self.world = n_nodes, rank, world
+        self.R = rows_per_rank(n_nodes, world)
+        self.lo, self.hi = row_range(n_nodes, rank, world)
+        rowptr, col = synth.rowgen_block(n_nodes, n_edges, self.lo, self.hi, device=device, **gen_kw)
+        if self.hi - self.lo < self.R:             # pad the last block with empty rows
+            rowptr = torch.cat([rowptr, rowptr[-1:].expand(self.R - (self.hi - self.lo))])
+        self.csr = CSR.from_arrays(rowptr, col, self.R * world)
+        t = torch.tensor([self.csr.nnz], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(t, group=group)
+        self.nnz_global = int(t.item())
+        self._norms(group)
+        return self
+
+    def _norms(self, group):
+        from ._lib import check, lib, ptr, stream_of
+        from .graph import NORM_INV_SQRT
+        L, dev, world = lib(), self.csr.device, self.world
+        self.nnz_local = self.csr.nnz
         self.dinv_local = self.csr.norm(NORM_INV_SQRT)                      # in-degrees of my rows are complete
         self.dinv_full = torch.empty(self.R * world, dtype=torch.float32, device=dev)
         if world > 1:
@@ -192,15 +263,16 @@ class PartitionedAPPNP:
             for t in self.peers.local:
                 t.zero_()
             return
-        self.full = torch.empty((R * P, self.ld), dtype=torch.float32, device=dev)
-        self.ping = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
-        self.pong = torch.zeros((R, self.ld), dtype=torch.float32, device=dev)
+        self.full = torch.empty((R * P, self.ld), dtype=dtype, device=dev)
+        self.ping = torch.zeros((R, self.ld), dtype=dtype, device=dev)
+        self.pong = torch.zeros((R, self.ld), dtype=dtype, device=dev)
         self._flip = False
 
         def spmm(x_full, z0_local, a, b):
             out = self.pong if self._flip else self.ping
             self._flip = not self._flip
-            ep = ops.make_epilogue(a=a, b=b, T=z0_local, ldt=z0_local.stride(0))
+            ep = (ops.make_epilogue(a=a, b=b, T=z0_local, ldt=z0_local.stride(0)) if b != 0.0
+                  else ops.make_epilogue(a=a))
             ops.spmm_raw(block.csr, x_full[:, :F], block.val, ep=ep, keep=(z0_local,), out=out[:, :F])
             return out
 
@@ -208,7 +280,8 @@ class PartitionedAPPNP:
         self.launches_per_hop = 1 + (2 if block.csr.n_items > 0 else 0)
 
     def run(self, z0_local: torch.Tensor, K: int, alpha: float) -> torch.Tensor:
-        """z0_local: [R, ld] (padded rows beyond N are zero).  Returns this rank's rows of z_K."""
+        """z0_local: [R, ld] (padded rows beyond N are zero).  Returns this rank's rows of z_K.
+        alpha = 0 is the plain K-hop GCN propagation A_hat^K z0 (no teleport read)."""
         if self.mode != "push":
             return self.driver.run(z0_local, K, 1.0 - alpha, alpha, self.full)
         from . import ops
@@ -217,8 +290,9 @@ class PartitionedAPPNP:
         dist.all_gather_into_tensor(full[0], z0_local, group=self.group)          # iterate 0 everywhere
         for k in range(K):
             src, nxt = full[k & 1], (k + 1) & 1
-            ep = ops.make_epilogue(a=1.0 - alpha, b=alpha, T=z0_local, ldt=z0_local.stride(0),
-                                   peers=self.peers.ptrs[nxt], peer_row0=blk.rank * R, ld_peer=self.ld)
+            tele = dict(b=alpha, T=z0_local, ldt=z0_local.stride(0)) if alpha != 0.0 else {}
+            ep = ops.make_epilogue(a=1.0 - alpha, peers=self.peers.ptrs[nxt], peer_row0=blk.rank * R,
+                                   ld_peer=self.ld, **tele)
             ops.spmm_raw(blk.csr, src[:, :F], blk.val, ep=ep, keep=(z0_local,), store_local=False)
             dist.all_reduce(self.tick, group=self.group)     # orders the hops: every push has landed
         return full[K & 1][blk.rank * R:(blk.rank + 1) * R]

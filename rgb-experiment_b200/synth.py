@@ -105,3 +105,57 @@ def make_graph(n_nodes: int, n_edges: int, n_feat: int, n_classes: int, *, seed:
 def make_named(name: str, **kw) -> SynthGraph:
     n, e, f, c = SHAPES[name]
     return make_graph(n, e, f, c, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# Row-generated directed graphs (papers100M-shaped, 111 M nodes / 3.2 B
+# edges): the in-neighbours of target row i are a pure function of (seed, i, k), so any rank can
+# generate exactly its own row block, as a CSR by construction (no edge list, no sort), and the
+# graph is identical for every partition count.
+# --------------------------------------------------------------------------------------------
+PAPERS100M = (111_059_956, 3_231_371_744, 128)     # nodes, directed edges, features
+
+
+def rowgen_degrees(n_nodes: int, n_edges: int, lo: int, hi: int, seed: int, device="cpu") -> torch.Tensor:
+    """In-degree (without the self loop) of rows [lo, hi): a Pareto-like law d = mean/2 * u^-1/2
+    clipped to [0, 64*mean], whose expectation is ~ the mean degree n_edges / n_nodes."""
+    mean = n_edges / n_nodes
+    idx = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    u = _uniform(idx, seed, 201).clamp_min(1e-12)
+    d = (0.5 * mean) * u.pow(-0.5)
+    return d.clamp_max(64.0 * mean).to(torch.int64)
+
+
+def rowgen_block(n_nodes: int, n_edges: int, lo: int, hi: int, *, seed: int = 20261018, device="cpu",
+                 skew: float = 2.0, locality: float = 0.0, self_loops: bool = True, rows_per_chunk: int = 1 << 21):
+    """CSR of target rows [lo, hi): rowptr int64 [hi-lo+1], col int32 [nnz] (global source ids).
+    Row i lists i itself first (the self loop GCN adds) and then deg_i sources: with probability
+    `locality` a node within +-N/64 of i, otherwise scramble(floor(N * u^skew)) -- popular sources
+    (a power law over columns) spread over the whole id range."""
+    deg = rowgen_degrees(n_nodes, n_edges, lo, hi, seed, device)
+    extra = 1 if self_loops else 0
+    rowptr = torch.zeros(hi - lo + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg + extra, 0, out=rowptr[1:])
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(nnz, dtype=torch.int32, device=device)
+    k_bits = max(1, math.ceil(math.log2(max(n_nodes, 2))))
+    for r0 in range(lo, hi, rows_per_chunk):
+        r1 = min(hi, r0 + rows_per_chunk)
+        d = deg[r0 - lo:r1 - lo] + extra
+        e0, e1 = int(rowptr[r0 - lo].item()), int(rowptr[r1 - lo].item())
+        rows = torch.repeat_interleave(torch.arange(r0, r1, dtype=torch.int64, device=device), d)
+        k = torch.arange(e0, e1, dtype=torch.int64, device=device) - rowptr[rows - lo]     # position inside the row
+        key = rows * 0x100000001B3 + k
+        u = _uniform(key, seed, 202)
+        c = (u.pow(skew) * n_nodes).to(torch.int64).clamp_max(n_nodes - 1)
+        c = (_mix(c + 0x51ED27) % (1 << k_bits)) * n_nodes >> k_bits            # scramble: hubs are not the low ids
+        if locality > 0:
+            near = _uniform(key, seed, 203) < locality
+            span = max(1, n_nodes // 64)
+            off = (_uniform(key, seed, 204) * (2 * span + 1)).to(torch.int64) - span
+            c = torch.where(near, (rows + off) % n_nodes, c)
+        if self_loops:
+            c = torch.where(k == 0, rows, c)
+        col[e0:e1] = c.to(torch.int32)
+        del rows, k, key, u, c
+    return rowptr, col

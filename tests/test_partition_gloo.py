@@ -74,3 +74,64 @@ def test_row_ranges_cover_all_rows():
                 assert lo <= hi and hi - lo <= PT.rows_per_rank(N, P)
                 seen += hi - lo
             assert seen == N
+
+
+def _grid_worker(rank, world, port, ret):
+    """2 row blocks x 2 feature slices: ranks sharing a feature slice exchange rows, feature slices
+    never communicate; the assembled result equals the single-process oracle bit for bit."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import rgb_experiment_b200.partition as PT
+        from oracle import pyg_restated as R
+        torch.manual_seed(0)
+        N, F, K, alpha = 103, 10, 4, 0.1
+        ei = torch.randint(N, (2, 1200))
+        ed, w = R.gcn_norm(ei, None, N, dtype=torch.float32)
+        z0 = torch.randn(N, F)
+        grid = PT.Grid(rank, world, 2)
+        assert (grid.Pr, grid.Pf, grid.rp, grid.fp) == (2, 2, rank // 2, rank % 2)
+        flo, fhi = grid.feature_slice(F)
+        assert (flo, fhi) == ((0, 8) if grid.fp == 0 else (8, 10))
+        assert [PT.Grid.feature_slice(grid, 47, fp=f) for f in range(2)] == [(0, 24), (24, 47)]
+        Rr = PT.rows_per_rank(N, grid.Pr)
+        lo, hi = PT.row_range(N, grid.rp, grid.Pr)
+        key, src = PT.local_edges(ed[0], ed[1], lo, hi)
+        wl = w[(ed[1] >= lo) & (ed[1] < hi)]
+
+        def spmm(x_full, z0_local, a, b):
+            out = torch.zeros(Rr, x_full.size(1)).index_add_(0, key.long(), wl.view(-1, 1) * x_full[src.long()])
+            return out * a + b * z0_local
+
+        z0_local = torch.zeros(Rr, fhi - flo)
+        z0_local[: hi - lo] = z0[lo:hi, flo:fhi]
+        drv = PT.PartitionedPropagator(N, grid.rp, grid.Pr, spmm, group=grid.row_group)
+        out_local = drv.run(z0_local, K, 1 - alpha, alpha)
+        pad = torch.zeros(Rr, 8)
+        pad[:, : fhi - flo] = out_local
+        allb = torch.empty(world * Rr, 8)
+        dist.all_gather_into_tensor(allb, pad)
+        allb = allb.view(world, Rr, 8)
+        full = torch.empty(Rr * grid.Pr, F)
+        for r in range(world):
+            a, b = (0, 8) if r % 2 == 0 else (8, 10)
+            full[(r // 2) * Rr:(r // 2 + 1) * Rr, a:b] = allb[r, :, : b - a]
+        ref = R.appnp_propagate(z0, ei, K, alpha)
+        ret[rank] = bool(torch.equal(full[:N], ref))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_by_feature_grid_matches_single_process_oracle():
+    world = 4
+    port = 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert all(ret.get(r) is True for r in range(world))

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--F", type=int, default=47)
     ap.add_argument("--K", type=int, default=10)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--feature-groups", type=int, default=1)
     args = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -35,14 +36,17 @@ def main():
     else:
         sg = S.make_named(args.workload, device=dev, features=False)
     N, F, K, alpha = sg.num_nodes, args.F, args.K, 0.1
-    blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, rank, world)
+    grid = PT.Grid(rank, world, args.feature_groups)
+    blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group)
     R = blk.R
+    flo, fhi = grid.feature_slice(F)
+    Fl = fhi - flo
     z0 = torch.randn(N, F, device=dev, generator=torch.Generator(device=dev).manual_seed(1))   # same on every rank
     res = {}
     for mode in ("allgather", "push"):
-        prop = PT.PartitionedAPPNP(blk, F, mode=mode)
+        prop = PT.PartitionedAPPNP(blk, Fl, group=grid.row_group, mode=mode)
         z0l = torch.zeros((R, prop.ld), device=dev)
-        z0l[: blk.hi - blk.lo, :F] = z0[blk.lo:blk.hi]
+        z0l[: blk.hi - blk.lo, :Fl] = z0[blk.lo:blk.hi, flo:fhi]
         out = prop.run(z0l, K, alpha).clone()
         for _ in range(2):
             prop.run(z0l, K, alpha)
@@ -56,19 +60,35 @@ def main():
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        full = torch.empty((R * world, prop.ld), device=dev)
-        dist.all_gather_into_tensor(full, out.contiguous())
-        res[mode] = (full[:N, :F].clone(), float(t.item()))
+        ldmax = torch.tensor([prop.ld], device=dev)
+        dist.all_reduce(ldmax, op=dist.ReduceOp.MAX)
+        ldm = int(ldmax.item())
+        mine = torch.zeros((R, ldm), device=dev)
+        mine[:, :prop.ld] = out
+        allb = torch.empty((world * R, ldm), device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        allb = allb.view(world, R, ldm)
+        y = torch.empty((R * grid.Pr, F), device=dev)
+        for r in range(world):                           # rank r = rp * Pf + fp holds rows block rp, feature slice fp
+            a, b = grid.feature_slice(F, fp=r % grid.Pf)
+            rp = r // grid.Pf
+            y[rp * R:(rp + 1) * R, a:b] = allb[r, :, :b - a]
+        res[mode] = (y[:N].clone(), float(t.item()))
         prop.close()
         del prop
     ok = {}
     if rank == 0:
         g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
         ref = P.ops.appnp(z0, g, K, alpha)
+        err = {}
         for mode, (y, ms) in res.items():
-            ok[mode] = bool(torch.equal(y, ref))
-        line = {"workload": args.workload, "N": N, "nnz": blk.nnz_global, "F": F, "K": K, "world": world,
-                "bit_equal_to_single_gpu": ok,
+            # bit-equal when the feature width (hence the launch shape and the split of long rows over a
+            # CTA's lane groups) matches the single-GPU run; a feature-sliced grid only reorders the partial
+            # sums of rows longer than 1024 edges -> held to the fp32 bar (1e-5 norm-wise) instead
+            err[mode] = float((y - ref).abs().max() / ref.abs().max())
+            ok[mode] = bool(torch.equal(y, ref)) if grid.Pf == 1 else err[mode] <= 1e-5
+        line = {"workload": args.workload, "N": N, "nnz": blk.nnz_global, "F": F, "K": K, "world": world, "grid": f"{grid.Pr}x{grid.Pf}",
+                "matches_single_gpu": ok, "relerr": err,
                 "ms_per_step": {m: round(v[1], 3) for m, v in res.items()},
                 "gteps": {m: round(blk.nnz_global * K / v[1] / 1e6, 2) for m, v in res.items()}}
         print(json.dumps(line), flush=True)
