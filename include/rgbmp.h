@@ -116,6 +116,17 @@ size_t rgbmp_row_order_workspace_bytes(int64_t n_rows);
 int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order,
                     void* ws, size_t ws_bytes, int device, void* stream);
 
+/* Sort an edge list by (row, col) and drop duplicate pairs = torch_sparse.coalesce(index, None, m, n)
+ * (rd2pd.py:93); with symmetrize = 1 the list is first extended by every reversed edge =
+ * torch_geometric.utils.to_undirected (itexperiments.py:235-238).  Two stable radix sorts (col, then
+ * row) + a flagged compaction; bit-exact against oracle.pyg_restated.coalesce / to_undirected.
+ * In : src,dst int64 [E].  Out: out_src,out_dst int64 [E or 2E capacity]; count_dev int64 [1] =
+ * number of pairs written, or -1 when an id falls outside [0, N). */
+size_t rgbmp_coalesce_workspace_bytes(int64_t E, int64_t N, int symmetrize);
+int rgbmp_coalesce(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int symmetrize,
+                   int64_t* out_src, int64_t* out_dst, int64_t* count_dev,
+                   void* ws, size_t ws_bytes, int device, void* stream);
+
 /* Column popularity and hot tagging (no reference counterpart; it steers the L2 so that the
  * feature rows gathered most often stay resident while once-touched rows stream through).
  *   rgbmp_col_freq: freq[c] = number of entries with col[k] == c   (int32 [n_cols], zeroed here)

@@ -79,6 +79,8 @@ def lib():
         "rgbmp_gat_backward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
                                          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
                                          C.c_int, c_vp]),
+        "rgbmp_coalesce_workspace_bytes": (c_sz, [c_i64, c_i64, C.c_int]),
+        "rgbmp_coalesce": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_peer_alloc": (C.c_int, [c_sz, c_vp, c_vp, C.c_int]),
         "rgbmp_peer_free": (C.c_int, [c_vp, C.c_int]),
         "rgbmp_peer_open": (C.c_int, [c_vp, c_vp, C.c_int]),

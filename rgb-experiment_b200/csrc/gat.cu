@@ -141,20 +141,30 @@ __device__ __forceinline__ void gat_fwd_range(const GatParams& p, int64_t k0, in
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
     int32_t cn = 0;
     if (off + G + gl < len) cn = __ldcs(col + off + G + gl);
-    const int nbmax = __reduce_max_sync(FULLMASK, nb);
-#pragma unroll 1
-    for (int j = 0; j < nbmax; j += U) {
+    if (G >= 2 * U && __all_sync(FULLMASK, nb == G)) {
+      // full batch in every group: software-pipelined, unpredicated -- the gathers of step j+U are in
+      // flight while step j is consumed (same structure as the SpMM main loop)
       float4 x[U];
       float as[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t c = (uint32_t)__shfl_sync(FULLMASK, cl, j + u, G);   // lanes past nb hold id 0: a valid row
+        const uint32_t c = (uint32_t)__shfl_sync(FULLMASK, cl, u, G);
         x[u] = __ldg(reinterpret_cast<const float4*>(xbase + (size_t)c * row_bytes));
         as[u] = __ldg(asb + (size_t)c * p.H);
       }
+#pragma unroll 1
+      for (int j = 0; j < G; j += U) {
+        float4 xn[U];
+        float asn[U];
+        const int jn = (j + U < G) ? j + U : j;      // last step re-requests itself (L1 hit, unused)
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (j + u < nb) {
+        for (int u = 0; u < U; ++u) {
+          const uint32_t c = (uint32_t)__shfl_sync(FULLMASK, cl, jn + u, G);
+          xn[u] = __ldg(reinterpret_cast<const float4*>(xbase + (size_t)c * row_bytes));
+          asn[u] = __ldg(asb + (size_t)c * p.H);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
           const float e = __expf(leaky_relu(as[u] + ad, p.slope) - M);
           s += e;
           const float w = p.drop ? e * __ldg(p.drop + (k0 + off + j + u) * p.H + h) : e;
@@ -162,6 +172,36 @@ __device__ __forceinline__ void gat_fwd_range(const GatParams& p, int64_t k0, in
           acc.y += w * x[u].y;
           acc.z += w * x[u].z;
           acc.w += w * x[u].w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          x[u] = xn[u];
+          as[u] = asn[u];
+        }
+      }
+    } else {
+      const int nbmax = __reduce_max_sync(FULLMASK, nb);
+#pragma unroll 1
+      for (int j = 0; j < nbmax; j += U) {
+        float4 x[U];
+        float as[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t c = (uint32_t)__shfl_sync(FULLMASK, cl, j + u, G);   // lanes past nb hold id 0: a valid row
+          x[u] = __ldg(reinterpret_cast<const float4*>(xbase + (size_t)c * row_bytes));
+          as[u] = __ldg(asb + (size_t)c * p.H);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u < nb) {
+            const float e = __expf(leaky_relu(as[u] + ad, p.slope) - M);
+            s += e;
+            const float w = p.drop ? e * __ldg(p.drop + (k0 + off + j + u) * p.H + h) : e;
+            acc.x += w * x[u].x;
+            acc.y += w * x[u].y;
+            acc.z += w * x[u].z;
+            acc.w += w * x[u].w;
+          }
         }
       }
     }

@@ -434,6 +434,51 @@ col_tag_kernel(const int32_t* __restrict__ col, int64_t nnz, const int32_t* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// coalesce / to_undirected: sort by (row, col), drop duplicates   
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+co_expand_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int64_t N, int symmetrize,
+                 int32_t* __restrict__ r, int32_t* __restrict__ c, int32_t* __restrict__ errflag) {
+  const int64_t n = symmetrize ? 2 * E : E;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool rev = i >= E;
+    const int64_t e = rev ? i - E : i;
+    const int64_t a = src[e], b = dst[e];
+    bad |= ((uint64_t)a >= (uint64_t)N) | ((uint64_t)b >= (uint64_t)N);
+    r[i] = (int32_t)(rev ? b : a);
+    c[i] = (int32_t)(rev ? a : b);
+  }
+  if (bad) atomicOr(errflag, 1);
+}
+
+__global__ void __launch_bounds__(256)
+co_flag_kernel(const int32_t* __restrict__ rs, const int32_t* __restrict__ cs, int64_t n, int32_t* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    flag[i] = (i == 0 || rs[i] != rs[i - 1] || cs[i] != cs[i - 1]) ? 1 : 0;
+}
+
+// pos = exclusive scan of the first-of-run flags; element i is a run head iff pos[i+1] != pos[i]
+__global__ void __launch_bounds__(256)
+co_write_kernel(const int32_t* __restrict__ rs, const int32_t* __restrict__ cs, int64_t n, const int32_t* __restrict__ pos,
+                const int32_t* __restrict__ errflag, int64_t* __restrict__ out_src, int64_t* __restrict__ out_dst,
+                int64_t* __restrict__ count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t last = n - 1;
+  const bool last_head = (n == 1) || rs[last] != rs[last - 1] || cs[last] != cs[last - 1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool head = (i == 0) || rs[i] != rs[i - 1] || cs[i] != cs[i - 1];
+    if (head) {
+      out_src[pos[i]] = rs[i];
+      out_dst[pos[i]] = cs[i];
+    }
+    if (i == last) *count = (*errflag) ? -1 : (int64_t)pos[last] + (last_head ? 1 : 0);
+  }
+}
+
 }  // namespace rgbmp
 
 using namespace rgbmp;
@@ -651,6 +696,80 @@ int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32
   row_key_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, window, keys);
   RGBMP_LAUNCH_CHECK("row_key_kernel");
   return sort_pairs_i32(keys, n_rows, 16 + wbits, kA, kB, vA, order, bh, sc32, nb, st);
+}
+
+static size_t coalesce_ws(int64_t n, int64_t N) {
+  (void)N;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  const size_t nb = (size_t)ceil_div((int64_t)nn, RS_TILE);
+  size_t b = 10 * align_up(nn * sizeof(int32_t), 256);                             // r, c, r1, c1, kA, kB, vA, p1, p2, flag
+  b += align_up(RS_BINS * nb * sizeof(int32_t), 256);
+  b += align_up(scan_ws_elems((int64_t)(RS_BINS * nb)) * sizeof(int32_t), 256);
+  b += align_up(scan_ws_elems((int64_t)nn) * sizeof(int32_t), 256);
+  return b + 4096;
+}
+
+size_t rgbmp_coalesce_workspace_bytes(int64_t E, int64_t N, int symmetrize) {
+  return coalesce_ws(symmetrize ? 2 * E : E, N);
+}
+
+int rgbmp_coalesce(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int symmetrize, int64_t* out_src,
+                   int64_t* out_dst, int64_t* count_dev, void* ws, size_t ws_bytes, int device, void* stream) {
+  if (E < 0 || N < 0 || !count_dev || !ws || (E > 0 && (!src || !dst || !out_src || !out_dst)))
+    return fail(RGBMP_EINVAL, "rgbmp_coalesce: null pointer or negative size");
+  const int64_t n = symmetrize ? 2 * E : E;
+  if (n >= (1ll << 31) - 1 || N >= (1ll << 31) - 1)
+    return fail(RGBMP_ERANGE, "rgbmp_coalesce: %lld entries or N=%lld exceeds int32", (long long)n, (long long)N);
+  if (ws_bytes < coalesce_ws(n, N)) return fail(RGBMP_EWORKSPACE, "rgbmp_coalesce: workspace");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_coalesce: bad device %d", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    RGBMP_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(int64_t), st));
+    return 0;
+  }
+  const size_t nn = (size_t)n;
+  const int64_t nb = ceil_div(n, RS_TILE);
+  Carver cv(ws, ws_bytes);
+  int32_t* r = cv.take<int32_t>(nn);
+  int32_t* c = cv.take<int32_t>(nn);
+  int32_t* r1 = cv.take<int32_t>(nn);
+  int32_t* c1 = cv.take<int32_t>(nn);
+  int32_t* kA = cv.take<int32_t>(nn);
+  int32_t* kB = cv.take<int32_t>(nn);
+  int32_t* vA = cv.take<int32_t>(nn);
+  int32_t* p1 = cv.take<int32_t>(nn);
+  int32_t* p2 = cv.take<int32_t>(nn);
+  int32_t* flag = cv.take<int32_t>(nn);
+  int32_t* bh = cv.take<int32_t>((size_t)RS_BINS * nb);
+  int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
+  int32_t* scf = cv.take<int32_t>(scan_ws_elems(n));
+  if (!cv.ok()) return fail(RGBMP_EWORKSPACE, "rgbmp_coalesce: workspace carve");
+  int32_t* err = bh;                       // one word, consumed before the histograms are written
+  RGBMP_CUDA(cudaMemsetAsync(err, 0, sizeof(int32_t), st));
+  int32_t* errkeep = scf + scan_ws_elems(n) - 1;   // last scratch word: survives until co_write
+  co_expand_kernel<<<kSMs * 8, 256, 0, st>>>(src, dst, E, N, symmetrize, r, c, err);
+  RGBMP_LAUNCH_CHECK("co_expand_kernel");
+  RGBMP_CUDA(cudaMemcpyAsync(errkeep, err, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < N) ++bits;
+  // LSD over the pair: stable sort by col, then stable sort by row
+  int rc = sort_pairs_i32(c, n, bits, kA, kB, vA, p1, bh, sc32, nb, st);
+  if (rc) return rc;
+  gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(r, p1, n, r1);
+  gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(c, p1, n, c1);
+  RGBMP_LAUNCH_CHECK("gather_i32_kernel");
+  rc = sort_pairs_i32(r1, n, bits, kA, kB, vA, p2, bh, sc32, nb, st);
+  if (rc) return rc;
+  gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(r1, p2, n, r);      // r, c now hold the sorted pairs
+  gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(c1, p2, n, c);
+  RGBMP_LAUNCH_CHECK("gather_i32_kernel");
+  co_flag_kernel<<<kSMs * 8, 256, 0, st>>>(r, c, n, flag);
+  RGBMP_LAUNCH_CHECK("co_flag_kernel");
+  RGBMP_CUDA(exclusive_scan<int32_t>(flag, n, scf, st));
+  co_write_kernel<<<kSMs * 8, 256, 0, st>>>(r, c, n, flag, errkeep, out_src, out_dst, count_dev);
+  RGBMP_LAUNCH_CHECK("co_write_kernel");
+  return 0;
 }
 
 int rgbmp_col_freq(const int32_t* col, int64_t nnz, int64_t n_cols, int32_t* freq, int device, void* stream) {

@@ -373,6 +373,9 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
 }
 
 constexpr int SPMM_THREADS = 256;
+#ifndef SPMM_MINB
+#define SPMM_MINB 1   // min CTAs per SM the short-row kernel is compiled for (register cap = 65536 / (256 * SPMM_MINB))
+#endif
 
 // per-lane vector bases: lane l of the group owns vectors l, l+G, ... of the feature tile
 template <typename T, int EPV, int G, int V>
@@ -389,7 +392,7 @@ __device__ __forceinline__ void lane_bases(const SpmmParams& p, int f0, const ch
 // Rows are taken in `row_order` (degree-sorted inside windows, built once per graph) so that the
 // groups sharing a warp run rows of equal length -- no idle issue slots from divergent trip counts.
 template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
-__global__ void __launch_bounds__(SPMM_THREADS) spmm_rows_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MINB) spmm_rows_kernel(const SpmmParams p) {
   constexpr int GPB = SPMM_THREADS / G;
   const int gl = threadIdx.x % G;
   const int64_t gid = (int64_t)blockIdx.x * GPB + threadIdx.x / G;

@@ -9,6 +9,7 @@ only ``build_local_csr`` / ``PartitionedAPPNP`` touch the CUDA library.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -62,9 +63,10 @@ class Grid:
 
 def auto_feature_groups(world: int, F: int) -> int:
     """Feature groups of the default grid.  The per-hop NVLink volume of a GPU shrinks with Pf while
-    rows get narrower (F/Pf); measured on 8 B200s with the products-shaped APPNP (F=47), see
-    profiles/r01_multigpu.txt."""
-    if world >= 8 and F >= 32:
+    rows get narrower (F/Pf).  Measured (profiles/r01_multigpu.txt): products-shaped APPNP F=47 --
+    4 GPUs 4x1 87.1 / 2x2 89.8 GTEPS, 8 GPUs 8x1 102 / 4x2 147 / 2x4 113; papers100M-shaped bf16
+    F=128 -- 4 GPUs 4x1 71 / 2x2 59 ms per hop."""
+    if world >= 4 and world % 2 == 0 and F >= 32:
         return 2
     return 1
 
@@ -288,13 +290,17 @@ class PartitionedAPPNP:
         blk, F, R = self.block, self.F, self.block.R
         full = self.peers.local
         dist.all_gather_into_tensor(full[0], z0_local, group=self.group)          # iterate 0 everywhere
+        # timing-only switches for attributing the hop time (results are WRONG with either of them set)
+        dbg_self_only = os.environ.get("RGBMP_DEBUG_PUSH") == "self"
+        dbg_no_tick = os.environ.get("RGBMP_DEBUG_TICK") == "0"
         for k in range(K):
             src, nxt = full[k & 1], (k + 1) & 1
             tele = dict(b=alpha, T=z0_local, ldt=z0_local.stride(0)) if alpha != 0.0 else {}
-            ep = ops.make_epilogue(a=1.0 - alpha, peers=self.peers.ptrs[nxt], peer_row0=blk.rank * R,
-                                   ld_peer=self.ld, **tele)
+            peers = [self.peers.ptrs[nxt][blk.rank]] if dbg_self_only else self.peers.ptrs[nxt]
+            ep = ops.make_epilogue(a=1.0 - alpha, peers=peers, peer_row0=blk.rank * R, ld_peer=self.ld, **tele)
             ops.spmm_raw(blk.csr, src[:, :F], blk.val, ep=ep, keep=(z0_local,), store_local=False)
-            dist.all_reduce(self.tick, group=self.group)     # orders the hops: every push has landed
+            if not dbg_no_tick:
+                dist.all_reduce(self.tick, group=self.group)     # orders the hops: every push has landed
         return full[K & 1][blk.rank * R:(blk.rank + 1) * R]
 
     def close(self):

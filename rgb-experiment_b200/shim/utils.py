@@ -135,22 +135,50 @@ def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
     raise ValueError(reduce)
 
 
+def _coalesce_cuda(index: torch.Tensor, N: int, symmetrize: bool) -> torch.Tensor:
+    """rgbmp_coalesce: (row, col)-sorted unique pairs of `index` (plus the reversed pairs).
+    The reference symmetrises BEFORE it moves the data to the device (itexperiments.py:235-238 vs
+    :258), so a host tensor is staged through the GPU and handed back on the host; without a CUDA
+    device this raises -- there is no CPU path."""
+    if not index.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("rgb-experiment_b200: to_undirected / coalesce need a CUDA device (no CPU path)")
+        return _coalesce_cuda(index.cuda(), N, symmetrize).to(index.device)
+    if index.dtype != torch.int64:
+        index = index.to(torch.int64)
+    L = lib()
+    dev = index.device
+    ei = index.contiguous()
+    E = ei.size(1)
+    cap = max((2 * E) if symmetrize else E, 1)
+    out = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    wsb = L.rgbmp_coalesce_workspace_bytes(E, N, int(symmetrize))
+    ws = _ws(wsb, dev)
+    check(L.rgbmp_coalesce(ptr(ei[0]) if E else None, ptr(ei[1]) if E else None, E, N, int(symmetrize), ptr(out[0]),
+                           ptr(out[1]), ptr(cnt), ptr(ws), ws.numel(), dev.index, stream_of(dev)), "coalesce")
+    n = int(cnt.item())
+    if n < 0:
+        raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
+    return out[:, :n]
+
+
 def coalesce(index, value, m, n, op="add"):
-    """torch_sparse.coalesce (rd2pd.py:93): sort by row*n+col, unique.  ("next" row f1)"""
+    """torch_sparse.coalesce (rd2pd.py:93): sort by row*n+col, unique.  CUDA radix-sort path when
+    there are no values (what the reference passes); values take the torch segmented reduce."""
+    if value is None:
+        return _coalesce_cuda(index, int(max(m, n)), False), None
+    _lib.require_cuda(index, "index")
     key = index[0] * n + index[1]
     uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
     out_index = torch.stack([uniq // n, uniq % n])
-    if value is None:
-        return out_index, None
     return out_index, scatter(value, inv, 0, uniq.numel(), "sum" if op == "add" else op)
 
 
 def to_undirected(edge_index, num_nodes=None):
-    """A16 (itexperiments.py:238).  ("next" row f1)"""
+    """A16 (itexperiments.py:238): symmetrise + coalesce on the device radix sort."""
     N = _num_nodes(edge_index, num_nodes)
-    row, col = edge_index[0], edge_index[1]
-    row, col = torch.cat([row, col]), torch.cat([col, row])
-    return coalesce(torch.stack([row, col]), None, N, N)[0]
+    return _coalesce_cuda(edge_index, N, True)
 
 
 def dropout_adj(edge_index, p=0.5, training=True):

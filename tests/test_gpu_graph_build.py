@@ -118,3 +118,34 @@ def test_to_undirected_and_coalesce_match_oracle():
     ei, n = CASES["loops_dups"]()
     assert torch.equal(U.to_undirected(ei.to(DEV), n).cpu(), R.to_undirected(ei, n))
     assert torch.equal(U.coalesce(ei.to(DEV), None, n, n)[0].cpu(), R.coalesce(ei, None, n, n)[0])
+
+
+@pytest.mark.parametrize("case", ["tiny", "loops_dups", "isolated", "hub", "empty", "single_node", "medium"])
+def test_to_undirected_and_coalesce_bit_exact(case):
+    """rgbmp_coalesce (two stable radix sorts + flagged compaction) against the oracle's sort/unique
+    restatement of torch_sparse.coalesce / torch_geometric.utils.to_undirected (A16)."""
+    import importlib
+    U = importlib.import_module("rgb_experiment_b200.shim.utils")
+    ei, n = CASES[case]()
+    ref_u = R.to_undirected(ei, n)
+    out_u = U.to_undirected(ei.to(DEV), n)
+    assert out_u.dtype == torch.int64 and out_u.is_cuda
+    assert torch.equal(out_u.cpu(), ref_u)
+    ref_c, _ = R.coalesce(ei, None, n, n)
+    out_c, v = U.coalesce(ei.to(DEV), None, n, n)
+    assert v is None and torch.equal(out_c.cpu(), ref_c)
+    # host input (the reference symmetrises before .to(device)): staged through the GPU, returned on the host
+    out_h = U.to_undirected(ei, n)
+    assert not out_h.is_cuda and torch.equal(out_h, ref_u)
+    # idempotent, symmetric
+    again = U.to_undirected(out_u, n)
+    assert torch.equal(again, out_u)
+    assert torch.equal(U.coalesce(out_u.flip(0), None, n, n)[0], out_u)
+
+
+def test_coalesce_rejects_out_of_range_ids():
+    import importlib
+    U = importlib.import_module("rgb_experiment_b200.shim.utils")
+    ei = torch.tensor([[0, 5, 2], [1, 2, 9]], device=DEV)
+    with pytest.raises(RuntimeError):
+        U.to_undirected(ei, 6)
