@@ -300,7 +300,8 @@ def main():
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("spmm_rows_kernel_bytes_per_launch")
+            # one "launch" of the roofline object = one hop = rows + long-row + combine kernels: report their summed DRAM bytes
+            roofline["traffic"] = json.load(open(tr)).get("hop_bytes_total")
         except Exception:
             pass
 

@@ -373,9 +373,16 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
 }
 
 constexpr int SPMM_THREADS = 256;
-#ifndef SPMM_MINB
-#define SPMM_MINB 1   // min CTAs per SM the short-row kernel is compiled for (register cap = 65536 / (256 * SPMM_MINB))
-#endif
+// Min CTAs per SM a variant is compiled for (register cap = 65536 / (256 * minb)).  ptxas is generous
+// with registers once the epilogue grew (86-93 for the main products variant -> 2 CTAs/SM, 4.16 ms instead
+// of 2.95 ms per hop); capping the variants whose in-flight gather data needs <= 32 registers at 64
+// costs no spills and restores 4 CTAs/SM.  Variants with more data in flight get proportionally more.
+template <int EPV, int V, int U, bool PIPE>
+constexpr int spmm_minb() {
+  constexpr int raw = ((EPV > 1) ? 4 : 1) * V * U * (PIPE ? 2 : 1);   // registers holding gathered vectors
+  constexpr int need = raw + V * EPV;                                  // + fp32 accumulators
+  return need <= 40 ? 4 : (need <= 56 ? 3 : (need <= 72 ? 2 : 1));
+}
 
 // per-lane vector bases: lane l of the group owns vectors l, l+G, ... of the feature tile
 template <typename T, int EPV, int G, int V>
@@ -392,7 +399,7 @@ __device__ __forceinline__ void lane_bases(const SpmmParams& p, int f0, const ch
 // Rows are taken in `row_order` (degree-sorted inside windows, built once per graph) so that the
 // groups sharing a warp run rows of equal length -- no idle issue slots from divergent trip counts.
 template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
-__global__ void __launch_bounds__(SPMM_THREADS, SPMM_MINB) spmm_rows_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(SPMM_THREADS, spmm_minb<EPV, V, U, PIPE>()) spmm_rows_kernel(const SpmmParams p) {
   constexpr int GPB = SPMM_THREADS / G;
   const int gl = threadIdx.x % G;
   const int64_t gid = (int64_t)blockIdx.x * GPB + threadIdx.x / G;
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, SPMM_MINB) spmm_rows_kernel(cons
 // long rows: one CTA per work item (<= long_chunk edges of one row); the CTA's groups take
 // contiguous sub-ranges, partial sums are reduced through shared memory in a fixed order.
 template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
-__global__ void __launch_bounds__(SPMM_THREADS) spmm_long_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(SPMM_THREADS, spmm_minb<EPV, V, U, PIPE>()) spmm_long_kernel(const SpmmParams p) {
   constexpr int Q = SPMM_THREADS / G;      // groups per CTA
   constexpr int W = G * V * EPV;           // feature tile width
   extern __shared__ float sm[];            // [Q][W]
