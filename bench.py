@@ -287,7 +287,7 @@ def main():
         return
 
     peak, peak_kind = peaks()
-    weighted = (world > 1) or not args.fold            # the partitioned path streams per-edge weights
+    weighted = (args.exchange == "allgather") if world > 1 else not args.fold   # the push path folds D^-1/2 too
     if world > 1:                                      # per GPU: nnz/Pr edges of F/Pf-wide rows
         hop_bytes = algorithmic_bytes_per_hop(nnz // grid.Pr, N // grid.Pr, F_local, weighted=weighted)
     else:

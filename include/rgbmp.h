@@ -168,6 +168,7 @@ typedef struct rgbmp_graph {
  *   if clamp: v = min(max(v,lo),hi)                                  (C&S post_step, A15)
  *   if reset_when==2 and reset_mask[i]: v = reset_val[i,:]           (C&S autoscale=False)
  *   Y[i,:] = v (if Y) ;  Y2[i,:] = out2_scale[i]*v (if Y2)           (pre-scaled copy for the next hop)
+ *   peer_out[q][peer_row0+i,:] = out2_scale ? out2_scale[i]*v : v    (fused all-gather, see below)
  */
 #define RGBMP_MAX_PEERS 8
 typedef struct rgbmp_epilogue {

@@ -46,11 +46,13 @@ static void choose_shape(int nvec, bool hbm_regime, int* G, int* V, int* U) {
     else { *G = 16; *V = 1; *U = 20; }
     return;
   }
-  int g = 1;
-  while (g < nvec) g <<= 1;
-  *G = g;
+  // narrow rows (products-shaped sweep at F = 8/16/24/32, profiles/r01_sweep_narrow.txt): 8 lanes with 4
+  // plain edges in flight for 5-8 vectors (F=24: 2.22 vs 2.50 ms pipelined), 4 lanes pipelined below
+  // that -- even for 1-2 vectors, where two idle lanes beat the 2-lane group (F=8: 1.33 vs 2.03 ms)
+  if (nvec > 4) { *G = 8; *V = 1; *U = 4; return; }
+  *G = 4;
   *V = 1;
-  *U = (g >= 4) ? 20 : 4;
+  *U = 20;
 }
 
 static int check_graph(const rgbmp_graph_t* g, const char* fn) {

@@ -361,15 +361,14 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
     s[i] = v;
   }
   if (p.Y) Raw<T, EPV>::store(reinterpret_cast<T*>(p.Y) + row * p.ldy + f, s, p.stream);
+  if (ep.out2_scale) {                     // pre-scaled copy (folded D^-1/2): what the NEXT hop gathers
+    const float s2 = __ldg(ep.out2_scale + row);
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) s[i] = __fmul_rn(s2, s[i]);
+    if (ep.Y2) Raw<T, EPV>::store(reinterpret_cast<T*>(ep.Y2) + row * ep.ldy2 + f, s, p.stream);
+  }
   for (int q = 0; q < ep.n_peers; ++q)   // fused all-gather: push the finished row to every peer over NVLink
     Raw<T, EPV>::store(reinterpret_cast<T*>(ep.peer_out[q]) + (ep.peer_row0 + row) * ep.ld_peer + f, s, 0);
-  if (ep.Y2) {
-    const float s2 = __ldg(ep.out2_scale + row);
-    float o[EPV];
-#pragma unroll
-    for (int i = 0; i < EPV; ++i) o[i] = __fmul_rn(s2, s[i]);
-    Raw<T, EPV>::store(reinterpret_cast<T*>(ep.Y2) + row * ep.ldy2 + f, o, p.stream);
-  }
 }
 
 constexpr int SPMM_THREADS = 256;

@@ -248,7 +248,8 @@ class PartitionedAPPNP:
     mode="push" (default on a multi-GPU box): ONE fused kernel per hop -- the SpMM's epilogue
     stores every finished row of the new iterate into ALL ranks' copies of the full iterate over
     NVLink (peer-mapped buffers, ping/pong), so the all-gather overlaps the aggregation row by row;
-    a 4-byte NCCL all-reduce orders the hops.
+    a 4-byte NCCL all-reduce orders the hops.  The normalisation is folded into row scalings (the
+    buffers hold D^-1/2 z, no per-edge weight stream) and the last hop stays local.
     mode="allgather": the baseline -- NCCL all_gather_into_tensor of the iterate rows, then the SpMM."""
 
     def __init__(self, block: LocalBlock, F: int, group=None, mode: str = "push", dtype=torch.float32):
@@ -262,6 +263,7 @@ class PartitionedAPPNP:
         if self.mode == "push":
             self.peers = PeerBuffers(R * P, self.ld, dtype, dev, block.rank, P, group, n_buf=2)
             self.tick = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.out = torch.zeros((R, self.ld), dtype=dtype, device=dev)
             for t in self.peers.local:
                 t.zero_()
             return
@@ -289,19 +291,28 @@ class PartitionedAPPNP:
         from . import ops
         blk, F, R = self.block, self.F, self.block.R
         full = self.peers.local
-        dist.all_gather_into_tensor(full[0], z0_local, group=self.group)          # iterate 0 everywhere
+        d = blk.dinv_local
+        # folded normalisation: the peer buffers hold u_k = D^-1/2 z_k (what the hop gathers, no per-edge
+        # weight stream); the epilogue rebuilds z_{k+1} = a * d_i * sum_j u_k[j] + b * z0_i and pushes d_i * z_{k+1}
+        u0 = ops.row_scale(z0_local, d)
+        dist.all_gather_into_tensor(full[0], u0, group=self.group)                # iterate 0 everywhere
         # timing-only switches for attributing the hop time (results are WRONG with either of them set)
         dbg_self_only = os.environ.get("RGBMP_DEBUG_PUSH") == "self"
         dbg_no_tick = os.environ.get("RGBMP_DEBUG_TICK") == "0"
         for k in range(K):
-            src, nxt = full[k & 1], (k + 1) & 1
+            src, nxt, last = full[k & 1], (k + 1) & 1, k == K - 1
             tele = dict(b=alpha, T=z0_local, ldt=z0_local.stride(0)) if alpha != 0.0 else {}
+            if last:                       # the result stays local and unscaled: no push, no tick
+                ep = ops.make_epilogue(row_scale=d, a=1.0 - alpha, **tele)
+                ops.spmm_raw(blk.csr, src[:, :F], None, ep=ep, keep=(z0_local, d), out=self.out[:, :F])
+                break
             peers = [self.peers.ptrs[nxt][blk.rank]] if dbg_self_only else self.peers.ptrs[nxt]
-            ep = ops.make_epilogue(a=1.0 - alpha, peers=peers, peer_row0=blk.rank * R, ld_peer=self.ld, **tele)
-            ops.spmm_raw(blk.csr, src[:, :F], blk.val, ep=ep, keep=(z0_local,), store_local=False)
+            ep = ops.make_epilogue(row_scale=d, a=1.0 - alpha, out2_scale=d, peers=peers, peer_row0=blk.rank * R,
+                                   ld_peer=self.ld, **tele)
+            ops.spmm_raw(blk.csr, src[:, :F], None, ep=ep, keep=(z0_local, d), store_local=False)
             if not dbg_no_tick:
                 dist.all_reduce(self.tick, group=self.group)     # orders the hops: every push has landed
-        return full[K & 1][blk.rank * R:(blk.rank + 1) * R]
+        return self.out
 
     def close(self):
         if self.mode == "push":

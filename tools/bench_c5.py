@@ -54,24 +54,32 @@ def main():
     z0l = torch.zeros((blk.R, prop.ld), dtype=dt, device=dev)
     z0l[: blk.hi - blk.lo, :Fl] = torch.randn(blk.hi - blk.lo, Fl, device=dev,
                                               generator=torch.Generator(device=dev).manual_seed(1 + rank)).to(dt)
-    for _ in range(args.warmup):
-        prop.run(z0l, args.hops, 0.0)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = prop.run(z0l, args.hops, 0.0)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    def timed(hops):
+        for _ in range(args.warmup):
+            prop.run(z0l, hops, 0.0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            o = prop.run(z0l, hops, 0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / args.steps, o
+
+    step_ms, out = timed(args.hops)
+    step_ms2, _ = timed(args.hops + 2)
+    t = torch.tensor([step_ms * args.steps], device=dev)
     finite = torch.tensor([1 if bool(torch.isfinite(out.float()).all()) else 0], device=dev)
     mem = torch.tensor([torch.cuda.max_memory_allocated(dev) / 2**30], device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(finite, op=dist.ReduceOp.MIN)
         dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    marginal = (step_ms2 - step_ms) / 2.0          # steady-state hop: the initial distribution of the iterate cancels
     ms_hop = float(t.item()) / (args.steps * args.hops)
     nnz = blk.nnz_global * (1 if grid.Pf == 1 else 1)        # every feature group walks the same edges once per hop
     if rank == 0:
@@ -80,6 +88,7 @@ def main():
                 "nnz": blk.nnz_global, "F": F, "dtype": args.dtype, "n_gpus": world, "grid": f"{grid.Pr}x{grid.Pf}",
                 "exchange": args.exchange, "locality": args.locality, "hops": args.hops, "ms_per_hop": round(ms_hop, 3),
                 "gteps": round(blk.nnz_global / ms_hop / 1e6, 2),
+                "steady_state_ms_per_hop": round(marginal, 3), "steady_state_gteps": round(blk.nnz_global / marginal / 1e6, 2),
                 "per_gpu_algorithmic_GBps": round(per_gpu_bytes / ms_hop / 1e6, 1),
                 "nvlink_rx_MB_per_hop_per_gpu": round((grid.Pr - 1) * blk.R * prop.ld * esz / 1e6, 1),
                 "build_s": round(build_s, 2), "torch_peak_mem_GiB": round(float(mem.item()), 1),

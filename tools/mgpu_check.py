@@ -79,9 +79,10 @@ def main():
     ok = {}
     if rank == 0:
         g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
-        ref = P.ops.appnp(z0, g, K, alpha)
+        refs = {"allgather": P.ops.appnp(z0, g, K, alpha), "push": P.ops.appnp(z0, g, K, alpha, True)}   # push folds D^-1/2
         err = {}
         for mode, (y, ms) in res.items():
+            ref = refs[mode]
             # bit-equal when the feature width (hence the launch shape and the split of long rows over a
             # CTA's lane groups) matches the single-GPU run; a feature-sliced grid only reorders the partial
             # sums of rows longer than 1024 edges -> held to the fp32 bar (1e-5 norm-wise) instead

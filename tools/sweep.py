@@ -40,6 +40,7 @@ def main():
                     "(L2 priority of hot / cold gathered rows: 0 normal, 1 evict-first, 2 evict-last)")
     ap.add_argument("--hot-mb", default="64", help="comma list of L2 budgets (MB) for the hot rows")
     ap.add_argument("--persist-mb", type=int, default=-1, help="set the persisting-L2 set-aside (MB) first")
+    ap.add_argument("--F", default="", help="override the feature widths of the workload plan, e.g. 8,16,24,32 (fp32)")
     ap.add_argument("--shapes", default="", help="only these G:V:U shapes, e.g. 8:2:18,16:1:20")
     args = ap.parse_args()
     import rgb_experiment_b200 as P
@@ -79,7 +80,8 @@ def main():
             print(json.dumps({"workload": wl, "N": N, "nnz": g.nnz, "max_deg": int(deg.max()), "n_long": g.fwd.n_long,
                               "n_items": g.fwd.n_items, "chunk": chunk, "long_chunk": lchunk, "window": window,
                               "policy": pol, "hot_mb": hot_mb}), flush=True)
-            for F, dt in plans[wl]:
+            plan = plans[wl] if not args.F else [(int(f), torch.float32) for f in args.F.split(",")]
+            for F, dt in plan:
                 x = torch.randn(N, F, device=dev).to(dt)
                 xb, ld = P.ops.as_rows(x)
                 esz = 2 if dt == torch.bfloat16 else 4
