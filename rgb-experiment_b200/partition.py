@@ -42,11 +42,16 @@ class Grid:
         self.rank, self.world, self.Pf, self.Pr = rank, world, feature_groups, world // feature_groups
         self.rp, self.fp = rank // feature_groups, rank % feature_groups
         self.row_group = None          # torch.distributed group of the ranks sharing my feature slice
+        self.col_group = None          # ... of the ranks sharing my row block (they hold the other slices)
         if world > 1 and feature_groups > 1:
             for f in range(feature_groups):   # every rank creates every group, in the same order
                 g = dist.new_group([r * feature_groups + f for r in range(self.Pr)])
                 if f == self.fp:
                     self.row_group = g
+            for r in range(self.Pr):
+                g = dist.new_group([r * feature_groups + f for f in range(feature_groups)])
+                if r == self.rp:
+                    self.col_group = g
 
     def feature_slice(self, F: int, align: int = 4, fp: Optional[int] = None):
         """[lo, hi) of the feature columns of feature group `fp` (default: mine).  Slices start on
@@ -120,7 +125,11 @@ class PartitionedPropagator:
 class LocalBlock:
     """This rank's CSR row block + normalisation, built by the integer kernels."""
 
-    def __init__(self, edge_index: torch.Tensor, N: int, loop_mode: int, rank: int, world: int, group=None):
+    def __init__(self, edge_index: torch.Tensor, N: int, loop_mode: int, rank: int, world: int, group=None,
+                 transpose_of: Optional["LocalBlock"] = None):
+        """transpose_of: build the block of the TRANSPOSED graph (rows = sources in my range, columns =
+        targets) for the backward pass; it reuses the forward block's D^-1/2 (the backward of
+        D^-1/2 A D^-1/2 is D^-1/2 A^T D^-1/2 with the same degree vector, also on directed graphs)."""
         from . import _lib
         from ._lib import check, lib, ptr, stream_of
         from .graph import CSR, NORM_INV_SQRT, _ws
@@ -141,10 +150,13 @@ class LocalBlock:
         self.N, self.rank, self.world = N, rank, world
         self.R = rows_per_rank(N, world)
         self.lo, self.hi = row_range(N, rank, world)
-        key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
+        if transpose_of is None:
+            key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
+        else:                                   # bucket by SOURCE: row = local source id, col = global target id
+            key, other = local_edges(e_dst[:nnz], e_src[:nnz], self.lo, self.hi)
         del e_src, e_dst
         self.csr = CSR(key, other, self.R, self.R * world)
-        self._norms(group)
+        self._norms(group, transpose_of)
 
     @classmethod
     def from_rowgen(cls, n_nodes: int, n_edges: int, rank: int, world: int, group=None, device=None, **gen_kw):
@@ -167,17 +179,20 @@ class LocalBlock:
         self._norms(group)
         return self
 
-    def _norms(self, group):
+    def _norms(self, group, transpose_of=None):
         from ._lib import check, lib, ptr, stream_of
         from .graph import NORM_INV_SQRT
         L, dev, world = lib(), self.csr.device, self.world
         self.nnz_local = self.csr.nnz
-        self.dinv_local = self.csr.norm(NORM_INV_SQRT)                      # in-degrees of my rows are complete
-        self.dinv_full = torch.empty(self.R * world, dtype=torch.float32, device=dev)
-        if world > 1:
-            dist.all_gather_into_tensor(self.dinv_full, self.dinv_local, group=group)
+        if transpose_of is not None:
+            self.dinv_local, self.dinv_full = transpose_of.dinv_local, transpose_of.dinv_full
         else:
-            self.dinv_full.copy_(self.dinv_local)
+            self.dinv_local = self.csr.norm(NORM_INV_SQRT)                  # in-degrees of my rows are complete
+            self.dinv_full = torch.empty(self.R * world, dtype=torch.float32, device=dev)
+            if world > 1:
+                dist.all_gather_into_tensor(self.dinv_full, self.dinv_local, group=group)
+            else:
+                self.dinv_full.copy_(self.dinv_local)
         self.val = torch.empty(max(self.nnz_local, 1), dtype=torch.float32, device=dev)
         check(L.rgbmp_gcn_edge_weight(ptr(self.csr.rowptr), ptr(self.csr.col), self.R, ptr(self.dinv_local),
                                       ptr(self.dinv_full), ptr(self.val), dev.index, stream_of(dev)),
@@ -252,10 +267,13 @@ class PartitionedAPPNP:
     buffers hold D^-1/2 z, no per-edge weight stream) and the last hop stays local.
     mode="allgather": the baseline -- NCCL all_gather_into_tensor of the iterate rows, then the SpMM."""
 
-    def __init__(self, block: LocalBlock, F: int, group=None, mode: str = "push", dtype=torch.float32):
+    def __init__(self, block: LocalBlock, F: int, group=None, mode: str = "push", dtype=torch.float32,
+                 ld: Optional[int] = None):
         from . import ops
         self.block, self.F, self.group, self.dtype = block, F, group, dtype
-        self.ld = ops.padded_width(F, dtype)
+        self.ld = ops.padded_width(F, dtype) if ld is None else int(ld)
+        if self.ld < ops.padded_width(F, dtype) or self.ld % ops.padded_width(1, dtype) != 0:
+            raise RuntimeError(f"ld={self.ld} is not a vector-aligned width >= F={F}")
         dev = block.csr.device
         R, P = block.R, block.world
         self.mode = mode if P > 1 else "allgather"
@@ -317,3 +335,74 @@ class PartitionedAPPNP:
     def close(self):
         if self.mode == "push":
             self.peers.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd over the partitioned propagation (distributed training epochs)
+# ------------------------------------------------------------------------------------------------
+class _DistKHop(torch.autograd.Function):
+    """z = M z0 on this rank's rows / feature slice; the map is linear, so the backward is the same
+    K-hop recursion on the transposed row block (nothing but the graph is saved)."""
+
+    @staticmethod
+    def forward(ctx, z0_local, fwd_run, bwd_run):
+        ctx.bwd_run = bwd_run
+        return fwd_run(z0_local.contiguous()).clone()
+
+    @staticmethod
+    def backward(ctx, dz):
+        return ctx.bwd_run(dz.contiguous()).clone(), None, None
+
+
+class _GatherSlices(torch.autograd.Function):
+    """[R, ld_slice] feature slices of the ranks that share a row block -> [R, F]; backward = own slice."""
+
+    @staticmethod
+    def forward(ctx, z_slice, grid: "Grid", F: int, col_group):
+        ctx.grid, ctx.F, ctx.ld = grid, F, z_slice.size(1)
+        if grid.Pf == 1:
+            return z_slice[:, :F]
+        parts = torch.empty((grid.Pf * z_slice.size(0), z_slice.size(1)), dtype=z_slice.dtype, device=z_slice.device)
+        dist.all_gather_into_tensor(parts, z_slice.contiguous(), group=col_group)
+        parts = parts.view(grid.Pf, z_slice.size(0), z_slice.size(1))
+        out = torch.empty((z_slice.size(0), F), dtype=z_slice.dtype, device=z_slice.device)
+        for f in range(grid.Pf):
+            a, b = grid.feature_slice(F, fp=f)
+            out[:, a:b] = parts[f, :, : b - a]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grid, F = ctx.grid, ctx.F
+        a, b = grid.feature_slice(F)
+        d = torch.zeros((dout.size(0), ctx.ld), dtype=dout.dtype, device=dout.device)
+        d[:, : b - a] = dout[:, a:b]
+        return d, None, None, None
+
+
+class DistAPPNP(torch.nn.Module):
+    """APPNP(K, alpha) over a process grid, differentiable: forward(h [R, F] rows of my row block) ->
+    [R, F] propagated rows.  Forward and backward each run the fused-push K-hop on their own row
+    block (forward CSR / transposed CSR); feature slices are re-assembled with one all-gather among
+    the Pf ranks of a row block.  `make_runner(block, F_slice)` builds the K-hop executor -- the CUDA
+    PartitionedAPPNP in production, a CPU stand-in in the gloo tests."""
+
+    def __init__(self, grid: "Grid", F: int, K: int, alpha: float, fwd_runner, bwd_runner, col_group=None, align: int = 4):
+        super().__init__()
+        self.grid, self.F, self.K, self.alpha = grid, F, K, alpha
+        self.fwd_runner, self.bwd_runner, self.col_group = fwd_runner, bwd_runner, col_group
+        self.ld = self.slice_ld(grid, F, align)
+
+    @staticmethod
+    def slice_ld(grid: "Grid", F: int, align: int = 4) -> int:
+        """Common leading dimension of every rank's feature-slice buffers (widest slice, vector aligned)."""
+        w = max(b - a for a, b in (grid.feature_slice(F, align, fp=f) for f in range(grid.Pf)))
+        return (w + align - 1) // align * align
+
+    def forward(self, h: torch.Tensor) -> torch.Tensor:
+        a, b = self.grid.feature_slice(self.F)
+        z0 = torch.zeros((h.size(0), self.ld), dtype=h.dtype, device=h.device)
+        z0[:, : b - a] = h[:, a:b]
+        z = _DistKHop.apply(z0, lambda t: self.fwd_runner(t, self.K, self.alpha),
+                            lambda t: self.bwd_runner(t, self.K, self.alpha))
+        return _GatherSlices.apply(z, self.grid, self.F, self.col_group)

@@ -135,3 +135,71 @@ def test_row_by_feature_grid_matches_single_process_oracle():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert all(ret.get(r) is True for r in range(world))
+
+
+def _dist_autograd_worker(rank, world, port, ret):
+    """DistAPPNP (differentiable K-hop over a 2x2 grid) with the CPU oracle standing in for the
+    kernels: forward rows and the gradient w.r.t. the input equal single-process autograd."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import rgb_experiment_b200.partition as PT
+        from oracle import pyg_restated as R
+        torch.manual_seed(0)
+        N, F, K, alpha = 97, 12, 3, 0.1
+        ei = torch.randint(N, (2, 800))                       # directed: the transpose really differs
+        ed, w = R.gcn_norm(ei, None, N, dtype=torch.float64)
+        h_full = torch.randn(N, F, dtype=torch.float64)
+        wgt = torch.randn(N, F, dtype=torch.float64)           # loss = sum(z * wgt)
+        grid = PT.Grid(rank, world, 2)
+        Rr = PT.rows_per_rank(N, grid.Pr)
+        lo, hi = PT.row_range(N, grid.rp, grid.Pr)
+
+        def make_runner(by_src):
+            tgt, oth = (ed[0], ed[1]) if by_src else (ed[1], ed[0])
+            m = (tgt >= lo) & (tgt < hi)
+            key, col, wl = (tgt[m] - lo), oth[m], w[m]
+
+            def spmm(x_full, z0_local, a, b):
+                out = torch.zeros(Rr, x_full.size(1), dtype=x_full.dtype).index_add_(0, key, wl.view(-1, 1) * x_full[col])
+                return out * a + b * z0_local
+
+            drv = PT.PartitionedPropagator(N, grid.rp, grid.Pr, spmm, group=grid.row_group)
+            return lambda t, K_, al: drv.run(t, K_, 1 - al, al)
+
+        a, b = grid.feature_slice(F)
+        mod = PT.DistAPPNP(grid, F, K, alpha, make_runner(False), make_runner(True), col_group=grid.col_group)
+        assert mod.ld == 8
+        h_loc = torch.zeros(Rr, F, dtype=torch.float64)
+        h_loc[: hi - lo] = h_full[lo:hi]
+        h_loc.requires_grad_(True)
+        z = mod(h_loc)
+        wl_ = torch.zeros(Rr, F, dtype=torch.float64)
+        wl_[: hi - lo] = wgt[lo:hi]
+        # every rank of a row block sees the same full-width rows; its backward only feeds its own slice
+        (z * wl_).sum().backward()
+        g = h_loc.grad.clone()
+        dist.all_reduce(g, group=grid.col_group)               # sum the slice-wise gradients of the row block
+        ho = h_full.clone().requires_grad_(True)
+        zo = R.appnp_propagate(ho, ei, K, alpha)
+        (zo * wgt).sum().backward()
+        ok_f = torch.allclose(z[: hi - lo].detach(), zo[lo:hi].detach(), rtol=1e-12, atol=1e-12)
+        ok_b = torch.allclose(g[: hi - lo], ho.grad[lo:hi], rtol=1e-12, atol=1e-12)
+        ret[rank] = bool(ok_f and ok_b)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dist_appnp_autograd_on_a_grid_matches_single_process():
+    world = 4
+    port = 33500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_dist_autograd_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert all(ret.get(r) is True for r in range(world))
