@@ -1,0 +1,143 @@
+"""Exact memoisation of no-grad aggregation calls.
+
+The reference evaluates the model twice per epoch with identical parameters and inputs
+(``test(model, ...)`` for the validation and then the test mask, itexperiments.py:464-473, body
+:600-626): every aggregation of the second forward repeats the first one bit for bit.  The caller
+cannot be changed, so the ops remember, per (graph, op, static arguments), the inputs and the
+result of recent no-grad calls and return the stored result when the SAME input values arrive
+again.
+
+"Same" is decided exactly: a cheap fingerprint (fp64 sum + eight strided samples per input, one
+small device->host read) selects a candidate, then ``torch.equal`` compares every input with the
+stored copy.  A fingerprint collision therefore costs one compare, never a wrong answer.  Stored
+results are handed out as clones and dropped when somebody modified them in place (``_version``).
+Only calls made with autograd disabled are memoised (training forwards never are), only when the
+aggregation is big enough for one extra read of its inputs to be noise (``MIN_WORK``), and the
+store is bounded in bytes (``RGBMP_EVAL_MEMO_MB``, default 4096; 0 turns the memo off).
+
+Pure host logic over torch tensors: nothing here touches the C ABI, so it is unit-tested on CPU.
+"""
+from __future__ import annotations
+
+import math
+import os
+import threading
+import weakref
+from collections import OrderedDict
+from typing import Callable, Sequence
+
+import torch
+
+MIN_WORK = 2e8          # nnz * F below which a call is cheaper than the bookkeeping (C1-sized graphs)
+MAX_ENTRIES = 64
+_budget_bytes = int(float(os.environ.get("RGBMP_EVAL_MEMO_MB", "4096")) * (1 << 20))
+_lock = threading.Lock()
+_store: "OrderedDict[tuple, _Entry]" = OrderedDict()
+_bytes = 0
+stats = {"hits": 0, "misses": 0, "skipped": 0, "evicted": 0}
+
+
+class _Entry:
+    __slots__ = ("owner", "inputs", "out", "out_version", "nbytes")
+
+    def __init__(self, owner, inputs, out):
+        self.owner = weakref.ref(owner)
+        self.inputs = inputs
+        self.out = out
+        self.out_version = out._version
+        self.nbytes = sum(t.numel() * t.element_size() for t in inputs) + out.numel() * out.element_size()
+
+
+def set_budget_mb(mb: float) -> None:
+    """Byte budget of the store; 0 disables the memo and drops everything held."""
+    global _budget_bytes
+    _budget_bytes = int(mb * (1 << 20))
+    if _budget_bytes <= 0:
+        clear()
+
+
+def enabled() -> bool:
+    return _budget_bytes > 0
+
+
+def clear() -> None:
+    global _bytes
+    with _lock:
+        _store.clear()
+        _bytes = 0
+
+
+def held_bytes() -> int:
+    return _bytes
+
+
+def fingerprint(tensors: Sequence[torch.Tensor]):
+    """Tuple of Python floats (one host sync for all inputs), or None when a value is not finite
+    (NaN never compares equal, so such inputs are simply not memoised)."""
+    parts = []
+    for t in tensors:
+        flat = t.reshape(-1) if t.is_contiguous() else t.flatten()
+        n = flat.numel()
+        if n == 0:
+            parts.append(torch.zeros(9, dtype=torch.float64, device=t.device))
+            continue
+        step = max(n // 8, 1)
+        sample = flat[::step][:8].to(torch.float64)
+        if sample.numel() < 8:
+            sample = torch.cat([sample, sample.new_zeros(8 - sample.numel())])
+        parts.append(torch.cat([t.sum(dtype=torch.float64).reshape(1), sample]))
+    vals = torch.cat(parts).tolist()
+    if not all(math.isfinite(v) for v in vals):
+        return None
+    return tuple(vals)
+
+
+def _evict_locked() -> None:
+    global _bytes
+    while _store and (_bytes > _budget_bytes or len(_store) > MAX_ENTRIES):
+        _, e = _store.popitem(last=False)
+        _bytes -= e.nbytes
+        stats["evicted"] += 1
+
+
+def _drop_locked(key) -> None:
+    global _bytes
+    e = _store.pop(key, None)
+    if e is not None:
+        _bytes -= e.nbytes
+
+
+def cached(owner, static_key: tuple, tensors: Sequence[torch.Tensor], work: float, fn: Callable[[], torch.Tensor]):
+    """Return fn(), or the stored result of an earlier no-grad call on `owner` (the graph object)
+    with the same static arguments and bit-identical input tensors."""
+    global _bytes
+    if torch.is_grad_enabled() or _budget_bytes <= 0 or work < MIN_WORK or \
+            2 * sum(t.numel() * t.element_size() for t in tensors) > _budget_bytes:
+        stats["skipped"] += 1
+        return fn()
+    fp = fingerprint(tensors)
+    if fp is None:
+        stats["skipped"] += 1
+        return fn()
+    key = (id(owner), static_key, tuple((tuple(t.shape), t.dtype) for t in tensors), fp)
+    with _lock:
+        e = _store.get(key)
+        if e is not None and (e.owner() is not owner or e.out._version != e.out_version):
+            _drop_locked(key)                    # id() reuse after the graph died, or result edited in place
+            e = None
+        if e is not None:
+            _store.move_to_end(key)
+    if e is not None and all(torch.equal(a, b) for a, b in zip(tensors, e.inputs)):
+        stats["hits"] += 1
+        return e.out.clone()
+    out = fn()
+    stats["misses"] += 1
+    if torch.is_tensor(out):
+        ent = _Entry(owner, tuple(t.detach().clone() for t in tensors), out.detach())
+        if ent.nbytes <= _budget_bytes:
+            with _lock:
+                _drop_locked(key)
+                _store[key] = ent
+                _bytes += ent.nbytes
+                _evict_locked()
+    return out

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, memo
 from ._lib import Epilogue, check, dtype_code, lib, ptr, stream_of
 from .graph import CSR, Graph, NORM_COUNT, NORM_INV_SQRT
 
@@ -169,8 +169,13 @@ class _Propagate(torch.autograd.Function):
         return spmm_raw(g.bwd, dy, g.gcn_val(True)), None, None
 
 
+def _work(graph: Graph, x: torch.Tensor) -> float:
+    return float(graph.nnz) * float(x.size(-1) if x.dim() > 1 else 1)
+
+
 def propagate(x: torch.Tensor, graph: Graph, kind: str = "sum") -> torch.Tensor:
-    return _Propagate.apply(x, graph, kind)
+    # memo.cached: the second of the caller's two identical eval forwards reuses the first
+    return memo.cached(graph, ("propagate", kind), (x,), _work(graph, x), lambda: _Propagate.apply(x, graph, kind))
 
 
 class _PropagateWeighted(torch.autograd.Function):
@@ -197,7 +202,8 @@ class _PropagateWeighted(torch.autograd.Function):
 
 
 def propagate_weighted(x, w, graph: Graph):
-    return _PropagateWeighted.apply(x, w, graph)
+    return memo.cached(graph, ("propagate_weighted",), (x, w), _work(graph, x),
+                       lambda: _PropagateWeighted.apply(x, w, graph))
 
 
 # ------------------------------------------------------------------------------------------
@@ -233,7 +239,9 @@ class _APPNP(torch.autograd.Function):
 def appnp(x, graph: Graph, K: int, alpha: float, fold: bool = False):
     if K == 0:
         return x
-    return _APPNP.apply(x, graph, int(K), float(alpha), bool(fold))
+    K, alpha, fold = int(K), float(alpha), bool(fold)
+    return memo.cached(graph, ("appnp", K, alpha, fold), (x,), K * _work(graph, x),
+                       lambda: _APPNP.apply(x, graph, K, alpha, fold))
 
 
 class _PowerHops(torch.autograd.Function):
@@ -251,7 +259,10 @@ class _PowerHops(torch.autograd.Function):
 
 
 def gcn_power(x, graph: Graph, K: int):
-    return x if K == 0 else _PowerHops.apply(x, graph, int(K))
+    if K == 0:
+        return x
+    return memo.cached(graph, ("gcn_power", int(K)), (x,), K * _work(graph, x),
+                       lambda: _PowerHops.apply(x, graph, int(K)))
 
 
 def dagnn_hops(x: torch.Tensor, graph: Graph, K: int) -> torch.Tensor:
@@ -492,7 +503,10 @@ class _GAT(torch.autograd.Function):
 def gat(xp, a_src, a_dst, graph: Graph, H: int, Cc: int, slope: float = 0.2, drop_edge: Optional[torch.Tensor] = None):
     """xp [N,H*C], a_src/a_dst [N,H] -> [N,H*C].  drop_edge: optional [nnz,H] keep-mask/(1-p) in EDGE order."""
     if gat_fusable(H, Cc):
-        drop_csr = graph.to_csr_order(drop_edge) if drop_edge is not None else None
+        if drop_edge is None:
+            return memo.cached(graph, ("gat", H, Cc, float(slope)), (xp, a_src, a_dst), _work(graph, xp),
+                               lambda: _GAT.apply(xp, a_src, a_dst, graph, H, Cc, float(slope), None))
+        drop_csr = graph.to_csr_order(drop_edge)
         return _GAT.apply(xp, a_src, a_dst, graph, H, Cc, float(slope), drop_csr)
     e = torch.nn.functional.leaky_relu(edge_u_add_v(a_src, a_dst, graph), slope)
     alpha = edge_softmax(e, graph)

@@ -392,6 +392,7 @@ class DistAPPNP(torch.nn.Module):
         self.grid, self.F, self.K, self.alpha = grid, F, K, alpha
         self.fwd_runner, self.bwd_runner, self.col_group = fwd_runner, bwd_runner, col_group
         self.ld = self.slice_ld(grid, F, align)
+        self.eval_memo, self._memo, self.memo_hits = True, None, 0
 
     @staticmethod
     def slice_ld(grid: "Grid", F: int, align: int = 4) -> int:
@@ -400,6 +401,24 @@ class DistAPPNP(torch.nn.Module):
         return (w + align - 1) // align * align
 
     def forward(self, h: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() or not self.eval_memo:
+            return self._propagate(h)
+        # the caller's two eval forwards per epoch are identical -- reuse the first result when EVERY
+        # rank sees bit-identical input rows again (the decision is all-reduced: a rank must never skip a collective
+        # that its peers enter)
+        memo = self._memo
+        same = memo is not None and memo[0].shape == h.shape and torch.equal(memo[0], h)
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=h.device)
+        if self.grid.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self.memo_hits += 1
+            return memo[1].clone()
+        out = self._propagate(h)
+        self._memo = (h.detach().clone(), out.detach().clone())
+        return out
+
+    def _propagate(self, h: torch.Tensor) -> torch.Tensor:
         a, b = self.grid.feature_slice(self.F)
         z0 = torch.zeros((h.size(0), self.ld), dtype=h.dtype, device=h.device)
         z0[:, : b - a] = h[:, a:b]

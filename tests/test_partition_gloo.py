@@ -186,7 +186,21 @@ def _dist_autograd_worker(rank, world, port, ret):
         (zo * wgt).sum().backward()
         ok_f = torch.allclose(z[: hi - lo].detach(), zo[lo:hi].detach(), rtol=1e-12, atol=1e-12)
         ok_b = torch.allclose(g[: hi - lo], ho.grad[lo:hi], rtol=1e-12, atol=1e-12)
-        ret[rank] = bool(ok_f and ok_b)
+        # f2: under no_grad the second identical forward is served from the memo on EVERY rank; when one rank's rows
+        # change, every rank recomputes (the decision is all-reduced, nobody skips a collective)
+        with torch.no_grad():
+            e1 = mod(h_loc.detach())
+            e2 = mod(h_loc.detach().clone())
+            hits_after_repeat = mod.memo_hits
+            h2 = h_loc.detach().clone()
+            if rank == 0:
+                h2[0, a] += 1.0
+            e3 = mod(h2)
+        ok_m = (hits_after_repeat == 1 and mod.memo_hits == 1 and torch.equal(e1, e2)
+                and torch.equal(e1, z.detach()))
+        changed = torch.tensor([0.0 if torch.equal(e3, e1) else 1.0])
+        dist.all_reduce(changed)
+        ret[rank] = bool(ok_f and ok_b and ok_m and changed.item() >= 1.0)
     finally:
         dist.destroy_process_group()
 
