@@ -87,6 +87,12 @@ def algorithmic_bytes_per_hop(nnz: int, n: int, F: int, weighted: bool) -> int:
     return nnz * (F * 4 + 4 + (4 if weighted else 0)) + n * F * 4 + (n + 1) * 8 + n * F * 4
 
 
+def workload_name(N: int, nnz: int, F: int) -> str:
+    """config.workload, shared by both arms (the reference arm runs a bounded sample of the same workload)."""
+    return (f"APPNP K={K_HOPS} alpha={ALPHA} propagate, ogbn-products-shaped R-MAT graph "
+            f"(N={N}, E={nnz - N} directed + {N} self loops, F={F} fp32)")
+
+
 def make_workload(device):
     import rgb_experiment_b200.synth as S
     return S.make_named(WORKLOAD, seed=GRAPH_SEED, device=device, features=False)
@@ -123,6 +129,7 @@ def run_reference(args, rank):
         return
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     sg = make_workload(dev)
+    N_full, nnz_full = sg.num_nodes, sg.edge_index.size(1) + sg.num_nodes      # the generator emits no self loops
     s, d, w, z, n_sub = cpu_sample(sg, dev)
     del sg
     cores = torch.get_num_threads()
@@ -138,11 +145,45 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "appnp_propagate_gteps", "value": val, "unit": "GTEPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}-shaped R-MAT graph, APPNP hop F={F_CLASSES} (CPU sample)"},
+            "config": {"workload": workload_name(N_full, nnz_full, F_CLASSES), "hops_per_step": 1, "nnz": nnz_full,
+                       "parallelism": f"{cores} host threads", "sample": sample},
             "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_epoch_guarded(rank, world, dev, line, limit_s=300):
+    """The second half of the BASELINE metric ("full-batch epoch ms at 1/2/4/8 GPU"): the reference's APPNPStack
+    epoch (1 train forward + backward + Adam, 2 eval forwards; itexperiments.py:417-473) on the same products-shaped
+    graph, measured by tools/bench_epoch.py AFTER the timed region and reported under "epoch".  It never costs the
+    headline line: an exception becomes {"error": ...}, and if nothing comes back within `limit_s` seconds (a rank
+    stuck in a collective) a watchdog prints the line without it and ends the process with status 0."""
+    import importlib.util
+    done = threading.Event()
+
+    def watchdog():
+        if done.wait(limit_s):
+            return
+        if line is not None:
+            line["epoch"] = {"error": f"no result within {limit_s} s"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
+        spec = importlib.util.spec_from_file_location("_bench_epoch", os.path.join(ROOT, "tools", "bench_epoch.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        res = mod.run(mod.default_args(), rank, world, dev)
+        res.pop("check_vs_single_gpu", None)
+    except Exception as e:                                        # noqa: BLE001 -- reported, never fatal for the line
+        res = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if line is None:                                          # a peer may now be waiting for me: leave quietly
+            done.set()
+            os._exit(0)
+    done.set()
+    return res
 
 
 def main():
@@ -152,6 +193,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-epoch", action="store_true",
+                    help="skip the full-batch epoch measurement (the second half of the BASELINE metric) after the timed region")
     ap.add_argument("--fold", type=int, default=1,
                     help="1 (default): D^-1/2 (A+I) D^-1/2 applied as row scalings around an unweighted sum (no per-edge "
                          "weight stream); 0: per-edge gcn_norm weights exactly as PyG multiplies them")
@@ -281,7 +324,13 @@ def main():
     if world > 1:
         torch.cuda.synchronize()
         prop.close()
+        del prop, blk
+    else:
+        del plan, g
+    torch.cuda.empty_cache()
     if rank != 0:
+        if not args.no_epoch:
+            run_epoch_guarded(rank, world, dev, None)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -328,15 +377,18 @@ def main():
     line = {"metric": "appnp_propagate_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"APPNP K={K_HOPS} alpha={ALPHA} propagate, ogbn-products-shaped R-MAT graph "
-                                   f"(N={N}, E={nnz - N} directed + {N} self loops, F={F} fp32)",
+            "config": {"workload": workload_name(N, nnz, F),
                        "hops_per_step": K_HOPS, "nnz": nnz, "parallelism": (f"{grid.Pr} row blocks x {grid.Pf} feature slices, exchange={args.exchange}"
                                        if world > 1 else "single"),
                        "l2": "inputs larger than L2 (features 470 MB, col 505 MB vs 126 MB L2)",
                        "norm": "per-edge weights" if weighted else "folded row scaling (same operator, no per-edge weight stream)", "graph_build_ms": build_ms},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.result()}
+    if not args.no_epoch:
+        line["epoch"] = run_epoch_guarded(rank, world, dev, line)
     print(json.dumps(line), flush=True)
+    if "error" in (line.get("epoch") or {}):
+        os._exit(0)                    # a failed epoch measurement may have left a collective half-entered
     if world > 1:
         dist.destroy_process_group()
 

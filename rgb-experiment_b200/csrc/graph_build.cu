@@ -2,6 +2,7 @@
 // degree normalisation, long-row work lists.  Bit-exact against oracle.pyg_restated
 // {edit_loops, csr_build, degree}.  All HBM-bound integer work: coalesced streaming reads,
 // shared-memory digit counters, grids sized from the data (one tile per CTA).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rgbmp {
@@ -266,6 +267,109 @@ rs_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict
   }
 }
 
+// v2 of the scatter: the tile is first reordered by digit in shared memory (same stable ranks), then written out
+// by consecutive threads -- every (tile, digit) run becomes one contiguous burst instead of 4-byte stores spread over
+// up to 32 bins per warp instruction.  Output positions are identical to v1 (bit-exact, stable).
+template <bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter2_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
+                   int64_t nblocks, const int32_t* __restrict__ blockoff /*scanned [256][nblocks]*/,
+                   int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+  __shared__ int32_t cnt[RS_WARPS][RS_BINS];
+  __shared__ int32_t dstart[RS_BINS];   // tile-local start of digit d
+  __shared__ int32_t gdelta[RS_BINS];   // global base of digit d for this tile - dstart[d]
+  __shared__ int32_t skey[RS_TILE];
+  __shared__ int32_t sval[RS_TILE];
+  __shared__ int32_t scan_sm[RS_THREADS / 32 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+
+  const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t wbase = tbase + (int64_t)warp * (32 * RS_ITEMS);
+  int32_t key[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    const bool valid = k < n;
+    key[r] = valid ? keys_in[k] : 0;
+    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    int32_t old = 0;
+    if (valid && lane == leader) {
+      old = cnt[warp][d];
+      cnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  int32_t tot = 0;
+  {  // thread d: exclusive scan over warps for digit d
+    const int d = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const int32_t c = cnt[w][d];
+      cnt[w][d] = tot;
+      tot += c;
+    }
+  }
+  int32_t tile_total;
+  const int32_t ds = block_exclusive_scan<int32_t, RS_THREADS>(tot, &tile_total, scan_sm);
+  dstart[threadIdx.x] = ds;
+  gdelta[threadIdx.x] = blockoff[(int64_t)threadIdx.x * nblocks + blockIdx.x] - ds;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    if (k < n) {
+      const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+      const int32_t lp = dstart[d] + cnt[warp][d] + rank[r];
+      skey[lp] = key[r];
+      sval[lp] = FIRST ? (int32_t)k : vals_in[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int j = i * RS_THREADS + threadIdx.x;
+    if (j < tile_total) {
+      const int32_t kk = skey[j];
+      const int32_t pos = gdelta[((uint32_t)kk >> shift) & 0xFF] + j;
+      keys_out[pos] = kk;
+      vals_out[pos] = sval[j];
+    }
+  }
+}
+
+// rowptr[r] = number of sorted keys < r = lower_bound(sorted, r), r in [0, N]: no atomics, no scan; neighbouring
+// rows walk nearly the same search path, so the probes are cache hits.
+__global__ void __launch_bounds__(256)
+rowptr_lower_bound_kernel(const int32_t* __restrict__ sorted, int64_t nnz, int64_t N, int64_t* __restrict__ rowptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > N) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(sorted + mid) < r) lo = mid + 1;
+    else hi = mid;
+  }
+  rowptr[r] = lo;
+}
+
+// 1 = first-round kernels (direct scatter, atomic degree histogram + scan), anything else = v2; read once.
+static int build_variant() {
+  static const int v = [] {
+    const char* e = getenv("RGBMP_BUILD_VARIANT");
+    return (e && e[0] == '1' && e[1] == 0) ? 1 : 2;
+  }();
+  return v;
+}
+
 __global__ void deg_hist_kernel(const int32_t* __restrict__ key, int64_t nnz, unsigned long long* __restrict__ deg) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride)
@@ -386,8 +490,10 @@ __global__ void longrow_fill_kernel(const int64_t* __restrict__ rowptr, int64_t 
 // stable LSD radix sort of (key, index) pairs on the low `bits` bits of the key; the permutation
 // (original index of every sorted element) lands in vfinal.  kA/kB/vA: scratch of n int32 each.
 static int sort_pairs_i32(const int32_t* key, int64_t n, int bits, int32_t* kA, int32_t* kB, int32_t* vA,
-                          int32_t* vfinal, int32_t* bh, int32_t* sc32, int64_t nb, cudaStream_t st) {
+                          int32_t* vfinal, int32_t* bh, int32_t* sc32, int64_t nb, cudaStream_t st,
+                          const int32_t** sorted_keys = nullptr) {
   const int passes = (bits + 7) / 8;
+  const bool v2 = build_variant() != 1;
   const int32_t* kin = key;
   const int32_t* vin = nullptr;
   for (int p = 0; p < passes; ++p) {
@@ -397,14 +503,18 @@ static int sort_pairs_i32(const int32_t* key, int64_t n, int bits, int32_t* kA, 
     rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, n, shift, nb, bh);
     RGBMP_LAUNCH_CHECK("rs_hist_kernel");
     RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
-    if (p == 0)
-      rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
-    else
-      rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+    if (p == 0) {
+      if (v2) rs_scatter2_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+      else rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+    } else {
+      if (v2) rs_scatter2_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+      else rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+    }
     RGBMP_LAUNCH_CHECK("rs_scatter_kernel");
     kin = kout;
     vin = vout;
   }
+  if (sorted_keys) *sorted_keys = kin;
   return 0;
 }
 
@@ -558,8 +668,6 @@ int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64
   if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_csr_build: bad device %d", device);
   cudaStream_t st = (cudaStream_t)stream;
 
-  // rowptr = exclusive scan of the key histogram (int64)
-  RGBMP_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int64_t), st));
   const size_t n = (size_t)(nnz > 0 ? nnz : 1);
   const int64_t nb = ceil_div((int64_t)n, RS_TILE);
   Carver cv(ws, ws_bytes);
@@ -570,18 +678,27 @@ int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64
   int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
   int64_t* sc64 = cv.take<int64_t>(scan_ws_elems(N + 1));
   if (!cv.ok()) return fail(RGBMP_EWORKSPACE, "rgbmp_csr_build: workspace carve");
-  if (nnz > 0) {
-    deg_hist_kernel<<<kSMs * 8, 256, 0, st>>>(key, nnz, (unsigned long long*)rowptr);
-    RGBMP_LAUNCH_CHECK("deg_hist_kernel");
+  const bool v2 = build_variant() != 1;
+  if (!v2 || nnz == 0) {
+    // rowptr = exclusive scan of the key histogram (int64)
+    RGBMP_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int64_t), st));
+    if (nnz > 0) {
+      deg_hist_kernel<<<kSMs * 8, 256, 0, st>>>(key, nnz, (unsigned long long*)rowptr);
+      RGBMP_LAUNCH_CHECK("deg_hist_kernel");
+    }
+    RGBMP_CUDA(exclusive_scan<int64_t>(rowptr, N + 1, sc64, st));
   }
-  RGBMP_CUDA(exclusive_scan<int64_t>(rowptr, N + 1, sc64, st));
   if (nnz == 0) return 0;
-  int rc_sort = 0;
 
   int bits = 1;
   while (bits < 31 && (1ll << bits) < N) ++bits;
-  rc_sort = sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st);
+  const int32_t* sorted = nullptr;
+  const int rc_sort = sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st, &sorted);
   if (rc_sort) return rc_sort;
+  if (v2) {   // rowptr straight from the sorted keys
+    rowptr_lower_bound_kernel<<<(unsigned)ceil_div(N + 1, 256), 256, 0, st>>>(sorted, nnz, N, rowptr);
+    RGBMP_LAUNCH_CHECK("rowptr_lower_bound_kernel");
+  }
   gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(other, eid, nnz, col);
   RGBMP_LAUNCH_CHECK("gather_i32_kernel");
   return 0;

@@ -392,7 +392,8 @@ class DistAPPNP(torch.nn.Module):
         self.grid, self.F, self.K, self.alpha = grid, F, K, alpha
         self.fwd_runner, self.bwd_runner, self.col_group = fwd_runner, bwd_runner, col_group
         self.ld = self.slice_ld(grid, F, align)
-        self.eval_memo, self._memo, self.memo_hits = True, None, 0
+        from . import memo as _memo_cfg
+        self.eval_memo, self._memo, self.memo_hits = _memo_cfg.enabled(), None, 0
 
     @staticmethod
     def slice_ld(grid: "Grid", F: int, align: int = 4) -> int:

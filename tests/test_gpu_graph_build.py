@@ -149,3 +149,47 @@ def test_coalesce_rejects_out_of_range_ids():
     ei = torch.tensor([[0, 5, 2], [1, 2, 9]], device=DEV)
     with pytest.raises(RuntimeError):
         U.to_undirected(ei, 6)
+
+
+def test_first_round_build_kernels_are_still_bit_exact():
+    """RGBMP_BUILD_VARIANT=1 selects the first-round kernels (direct scatter, atomic degree histogram);
+    the variant is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_gpu_graph_build as T\n"
+        "from helpers import CASES\n"
+        "for case in ('loops_dups', 'hub', 'medium', 'isolated'):\n"
+        "    ei, n = CASES[case]()\n"
+        "    T.check_graph(ei, n, 2)\n"
+        "print('variant1 ok')\n" % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, RGBMP_BUILD_VARIANT="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant1 ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_products_sized_build_properties():
+    """Full BASELINE size (123.7 M edges): size-independent properties of the CSR -- rows sorted and
+    stable (eid increasing inside a row), rowptr = histogram prefix, col/eid consistent with the edited
+    list, transpose CSR a permutation of the same edges."""
+    P = product()
+    import rgb_experiment_b200.synth as S
+    sg = S.make_named("products", device=DEV, features=False)
+    n = sg.num_nodes
+    g = P.Graph(sg.edge_index, n, P.LOOP_ADD_REMAINING)
+    assert g.nnz == sg.edge_index.size(1) + n                     # the generator emits no self loops
+    for csr, key, other in ((g.fwd, g.e_dst, g.e_src), (g.bwd, g.e_src, g.e_dst)):
+        eid = csr.eid.long()
+        assert int(csr.rowptr[0]) == 0 and int(csr.rowptr[-1]) == g.nnz
+        deg = torch.bincount(key.long(), minlength=n)
+        assert torch.equal(csr.rowptr[1:] - csr.rowptr[:-1], deg)
+        skey = key[eid]
+        assert bool((skey[1:] >= skey[:-1]).all())                 # sorted by key
+        same = skey[1:] == skey[:-1]
+        assert bool((eid[1:][same] > eid[:-1][same]).all())        # stable: input order inside a row
+        assert torch.equal(csr.col, other[eid])
+        assert torch.equal(torch.sort(eid).values, torch.arange(g.nnz, device=DEV))   # a permutation
+        del eid, skey, same, deg

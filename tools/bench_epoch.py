@@ -64,6 +64,23 @@ def main():
     dev = torch.device("cuda", lr_)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    res = run(args, rank, world, dev)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def default_args(**kw):
+    """The argument set of main() as a namespace (bench.py calls run() with it)."""
+    d = dict(workload="products", hidden=64, K=10, alpha=0.1, epochs=5, warmup=2, feature_groups=0, check=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def run(args, rank, world, dev):
+    """One measurement; needs an initialised NCCL process group when world > 1.  Returns the result dict
+    (identical on every rank up to the accuracies, which rank 0 reports)."""
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.partition as PT
     import rgb_experiment_b200.synth as S
@@ -199,18 +216,18 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.epochs, wall], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(json.dumps({"config": "APPNPStack full-batch epoch (1 train fwd+bwd+Adam, 2 eval fwd), "
-                                    f"{args.workload}-shaped, hidden {args.hidden}, K={args.K}",
-                          "n_gpus": world, "grid": "1x1" if grid is None else f"{grid.Pr}x{grid.Pf}",
-                          "epoch_ms": round(ms[0].item(), 2), "epoch_wall_ms": round(ms[1].item(), 2),
-                          "val_acc": round(v[0], 4), "test_acc": round(t[0], 4), "val_loss": round(v[1], 4),
-                          "check_vs_single_gpu": check}), flush=True)
+    import rgb_experiment_b200.memo as memo
+    res = {"config": "APPNPStack full-batch epoch (1 train fwd+bwd+Adam, 2 eval fwd), "
+                     f"{args.workload}-shaped, hidden {args.hidden}, K={args.K}",
+           "n_gpus": world, "grid": "1x1" if grid is None else f"{grid.Pr}x{grid.Pf}",
+           "epoch_ms": round(ms[0].item(), 2), "epoch_wall_ms": round(ms[1].item(), 2),
+           "eval_memo": memo.enabled(), "val_acc": round(v[0], 4), "test_acc": round(t[0], 4),
+           "val_loss": round(v[1], 4), "check_vs_single_gpu": check}
     if world > 1:
         torch.cuda.synchronize()
         pf.close()
         pb.close()
-        dist.destroy_process_group()
+    return res
 
 
 if __name__ == "__main__":
