@@ -15,6 +15,15 @@ Only calls made with autograd disabled are memoised (training forwards never are
 aggregation is big enough for one extra read of its inputs to be noise (``MIN_WORK``), and the
 store is bounded in bytes (``RGBMP_EVAL_MEMO_MB``, default 4096; 0 turns the memo off).
 
+Generations: a grad-enabled call that follows no-grad calls starts a new training phase, after
+which the optimiser moves the parameters and the stored eval inputs go stale.  A miss therefore
+first drops the entries of the same (graph, op, arguments, shapes) that were last stored or hit
+more than one training phase ago -- their device memory goes back to the allocator before the new
+result is computed, so a training loop holds two generations of entries instead of filling the
+byte budget with dead ones (measured on the products-shaped APPNP epoch: without this the first
+epochs pay fresh 0.9 GB cudaMallocs, 121 instead of 88 ms for the training step).  Entries that
+keep hitting (an aggregation of the raw input features, identical in every epoch) never age.
+
 Pure host logic over torch tensors: nothing here touches the C ABI, so it is unit-tested on CPU.
 """
 from __future__ import annotations
@@ -34,13 +43,16 @@ _budget_bytes = int(float(os.environ.get("RGBMP_EVAL_MEMO_MB", "4096")) * (1 << 
 _lock = threading.Lock()
 _store: "OrderedDict[tuple, _Entry]" = OrderedDict()
 _bytes = 0
-stats = {"hits": 0, "misses": 0, "skipped": 0, "evicted": 0}
+_gen = 0                 # number of training phases (runs of grad-enabled calls) seen so far
+_in_train = False
+stats = {"hits": 0, "misses": 0, "skipped": 0, "evicted": 0, "stale_dropped": 0}
 
 
 class _Entry:
-    __slots__ = ("owner", "inputs", "out", "out_version", "nbytes")
+    __slots__ = ("owner", "inputs", "out", "out_version", "nbytes", "gen")
 
     def __init__(self, owner, inputs, out):
+        self.gen = _gen
         self.owner = weakref.ref(owner)
         self.inputs = inputs
         self.out = out
@@ -110,7 +122,12 @@ def _drop_locked(key) -> None:
 def cached(owner, static_key: tuple, tensors: Sequence[torch.Tensor], work: float, fn: Callable[[], torch.Tensor]):
     """Return fn(), or the stored result of an earlier no-grad call on `owner` (the graph object)
     with the same static arguments and bit-identical input tensors."""
-    global _bytes
+    global _bytes, _gen, _in_train
+    if torch.is_grad_enabled():
+        if not _in_train:
+            _gen, _in_train = _gen + 1, True
+    else:
+        _in_train = False
     if torch.is_grad_enabled() or _budget_bytes <= 0 or work < MIN_WORK or \
             2 * sum(t.numel() * t.element_size() for t in tensors) > _budget_bytes:
         stats["skipped"] += 1
@@ -119,7 +136,8 @@ def cached(owner, static_key: tuple, tensors: Sequence[torch.Tensor], work: floa
     if fp is None:
         stats["skipped"] += 1
         return fn()
-    key = (id(owner), static_key, tuple((tuple(t.shape), t.dtype) for t in tensors), fp)
+    family = (id(owner), static_key, tuple((tuple(t.shape), t.dtype) for t in tensors))
+    key = family + (fp,)
     with _lock:
         e = _store.get(key)
         if e is not None and (e.owner() is not owner or e.out._version != e.out_version):
@@ -129,7 +147,12 @@ def cached(owner, static_key: tuple, tensors: Sequence[torch.Tensor], work: floa
             _store.move_to_end(key)
     if e is not None and all(torch.equal(a, b) for a, b in zip(tensors, e.inputs)):
         stats["hits"] += 1
+        e.gen = _gen
         return e.out.clone()
+    with _lock:                                  # stale generation of this call site: free it before computing
+        for k in [k for k, v in _store.items() if k[:3] == family and v.gen < _gen - 1]:
+            _drop_locked(k)
+            stats["stale_dropped"] += 1
     out = fn()
     stats["misses"] += 1
     if torch.is_tensor(out):

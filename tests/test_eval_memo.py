@@ -129,3 +129,22 @@ def test_store_is_bounded_in_bytes_and_dies_with_the_owner():
                 M.cached(o, ("op",), (x,), BIG, lambda: f(x))
                 assert len(calls) == n + 1
                 break
+
+
+def test_a_training_forward_makes_the_previous_generation_droppable():
+    """Epoch loop: train forward (grad on), eval, eval.  Each epoch's eval inputs differ (the optimiser stepped);
+    the store must hold two generations, not one per epoch; inputs that keep hitting never age."""
+    g, calls = _Owner(), []
+    f = _op(calls)
+    raw = torch.randn(40, 5)                            # an aggregation of the raw features: same in every epoch
+    for epoch in range(5):
+        x = torch.randn(40, 5) + epoch                  # depends on the parameters: new values every epoch
+        M.cached(g, ("op",), (x,), BIG, lambda: f(x))   # training forward (grad enabled): a new generation ...
+        M.cached(g, ("op2",), (x,), BIG, lambda: f(x))  # ... once per training phase, however many layers pass
+        with torch.no_grad():
+            for _ in range(2):
+                M.cached(g, ("op",), (x,), BIG, lambda: f(x))
+                M.cached(g, ("op",), (raw,), BIG, lambda: f(raw))
+        assert len(M._store) == min(epoch, 1) + 2       # this and the previous epoch's x + raw, nothing older
+    # per epoch: x misses once and hits once; raw misses only in the first epoch
+    assert M.stats["misses"] == 5 + 1 and M.stats["hits"] == 5 + 9 and M.stats["stale_dropped"] == 3

@@ -36,7 +36,7 @@ def out(**kw):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="build,c2,c3,c4")
+    ap.add_argument("--only", default="build,c1,c2,c3,c4")
     args = ap.parse_args()
     only = set(args.only.split(","))
     import rgb_experiment_b200 as P
@@ -60,6 +60,45 @@ def main():
             out(config="graph_build(edit+CSR+transpose CSR)", workload=wl, E=sg.edge_index.size(1), ms=min(ts),
                 Medges_per_s=sg.edge_index.size(1) / min(ts) / 1e3)
             del sg
+
+    if "c1" in only:
+        # BASELINE configs[0]: GCN 2-layer hidden 64 on the Cora-shaped graph.  4 MB per hop: latency-bound, so the
+        # numbers that matter are microseconds per call and launches per epoch, not a roofline fraction.
+        sg = S.make_named("cora", device=dev)
+        N = sg.num_nodes
+
+        class GCN(nn.Module):        # models/gcn.py:18-31: GCNConv -> BatchNorm -> GCNConv, no ReLU / dropout between
+            def __init__(self):
+                super().__init__()
+                self.c1, self.c2 = L.GCNConv(sg.x.size(1), 64), L.GCNConv(64, sg.num_classes)
+                self.bn = nn.BatchNorm1d(64)
+
+            def forward(self, x, ei):
+                return F.log_softmax(self.c2(self.bn(self.c1(x, ei)), ei), 1)
+
+        m = GCN().to(dev)
+        opt = torch.optim.Adam(m.parameters(), lr=0.01)
+        tr = torch.arange(N, device=dev) % 10 < 6
+
+        def epoch():
+            m.train()
+            opt.zero_grad()
+            F.nll_loss(m(sg.x, sg.edge_index)[tr], sg.y[tr]).backward()
+            opt.step()
+            m.eval()
+            with torch.no_grad():
+                m(sg.x, sg.edge_index)
+                m(sg.x, sg.edge_index)
+
+        ms = ev_ms(epoch, 50, 5)
+        g = P.get_graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
+        x64 = torch.randn(N, 64, device=dev)
+        hop = ev_ms(lambda: P.ops.propagate(x64, g, "gcn"), 200, 20)
+        khop = ev_ms(lambda: P.ops.appnp(x64[:, :7].contiguous(), g, 10, 0.1), 100, 10)
+        out(config="C1 GCN 2-layer hidden 64 Cora-shaped", nnz=g.nnz, epoch_ms=ms, hop_F64_us=hop * 1e3,
+            appnp_K10_F7_us=khop * 1e3, aggregation_launches_per_epoch=2 + 2 + 2 * 2,
+            note="latency-bound (4 MB per hop): 2 train-forward + 2 backward + 2x2 eval SpMM launches per epoch, graph built once")
+        del sg, g, m
 
     if "c2" in only:
         sg = S.make_named("arxiv", device=dev)

@@ -163,11 +163,23 @@ def run(args, rank, world, dev):
             dist.all_reduce(stat, group=grid.row_group)
         return stat[0].item() / n_glob[key], stat[1].item()       # .item(): the reference syncs per eval too
 
+    phase_ev = []                                                  # CUDA events at the phase boundaries of every epoch
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
     def epoch():
+        ev = [mark()]
         loss, _ = train_step()
         loss.item()                                                # train_losses.append(loss.item())
+        ev.append(mark())
         v = eval_step("val")
+        ev.append(mark())
         t = eval_step("test")
+        ev.append(mark())
+        phase_ev.append(ev)
         return v, t
 
     check = None
@@ -217,11 +229,17 @@ def run(args, rank, world, dev):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     import rgb_experiment_b200.memo as memo
+    timed = phase_ev[-args.epochs:]
+    phases = [round(sum(ev[i].elapsed_time(ev[i + 1]) for ev in timed) / len(timed), 2) for i in range(3)]
+    per_epoch = [[round(ev[i].elapsed_time(ev[i + 1]), 1) for i in range(3)] for ev in phase_ev]
     res = {"config": "APPNPStack full-batch epoch (1 train fwd+bwd+Adam, 2 eval fwd), "
                      f"{args.workload}-shaped, hidden {args.hidden}, K={args.K}",
            "n_gpus": world, "grid": "1x1" if grid is None else f"{grid.Pr}x{grid.Pf}",
            "epoch_ms": round(ms[0].item(), 2), "epoch_wall_ms": round(ms[1].item(), 2),
-           "eval_memo": memo.enabled(), "val_acc": round(v[0], 4), "test_acc": round(t[0], 4),
+           "phase_ms": {"train_fwd_bwd_step": phases[0], "eval_val": phases[1], "eval_test": phases[2]},
+           "phase_ms_per_epoch_incl_warmup": per_epoch if os.environ.get("RGBMP_EPOCH_TRACE") else None,
+           "eval_memo": memo.enabled(), "memo_stats": dict(memo.stats) if world == 1 else {"hits": dist_prop.memo_hits},
+           "val_acc": round(v[0], 4), "test_acc": round(t[0], 4),
            "val_loss": round(v[1], 4), "check_vs_single_gpu": check}
     if world > 1:
         torch.cuda.synchronize()
