@@ -161,6 +161,60 @@ ee_write_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst
   }
 }
 
+// v2 of the write: coalesced loads (lane-consecutive edges, EE_ITEMS rounds), ballot ranks give every kept edge its
+// stable slot inside the tile, the tile is compacted in shared memory and leaves as one contiguous burst.
+__global__ void __launch_bounds__(EE_THREADS)
+ee_write2_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int filter,
+                 const int32_t* __restrict__ blockoff, int32_t* __restrict__ e_src, int32_t* __restrict__ e_dst) {
+  constexpr int W = EE_THREADS / 32;
+  __shared__ int32_t woff[EE_ITEMS * W];          // kept edges per (round, warp) -> exclusive offsets
+  __shared__ int32_t ss[EE_TILE], sd[EE_TILE];
+  __shared__ int32_t total_sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * EE_TILE;
+  int32_t s[EE_ITEMS], d[EE_ITEMS];
+  uint32_t bal[EE_ITEMS];
+#pragma unroll
+  for (int i = 0; i < EE_ITEMS; ++i) {
+    const int64_t e = base + (int64_t)i * EE_THREADS + threadIdx.x;
+    bool keep = false;
+    s[i] = d[i] = 0;
+    if (e < E) {
+      s[i] = (int32_t)src[e];
+      d[i] = (int32_t)dst[e];
+      keep = (!filter || s[i] != d[i]);
+    }
+    bal[i] = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) woff[i * W + warp] = __popc(bal[i]);
+  }
+  __syncthreads();
+  if (warp == 0) {                                 // exclusive scan of the EE_ITEMS * W (= 64) counters, 2 per lane
+    static_assert(EE_ITEMS * W == 64, "scan below assumes 64 counters");
+    const int32_t a = woff[2 * lane], b = woff[2 * lane + 1];
+    const int32_t inc = warp_inclusive_scan<int32_t>(a + b, lane);
+    woff[2 * lane] = inc - a - b;
+    woff[2 * lane + 1] = inc - b;
+    if (lane == 31) total_sm = inc;
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < EE_ITEMS; ++i) {
+    if ((bal[i] >> lane) & 1u) {
+      const int32_t p = woff[i * W + warp] + __popc(bal[i] & lt);
+      ss[p] = s[i];
+      sd[p] = d[i];
+    }
+  }
+  __syncthreads();
+  const int32_t total = total_sm;
+  const int64_t out0 = blockoff[blockIdx.x];
+  for (int j = threadIdx.x; j < total; j += EE_THREADS) {
+    e_src[out0 + j] = ss[j];
+    e_dst[out0 + j] = sd[j];
+  }
+}
+
 // the count kernel must see the same thread->edge mapping only in aggregate (per block), so the
 // strided mapping there is fine; both kernels cover edges [block*TILE, (block+1)*TILE).
 
@@ -270,16 +324,18 @@ rs_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict
 // v2 of the scatter: the tile is first reordered by digit in shared memory (same stable ranks), then written out
 // by consecutive threads -- every (tile, digit) run becomes one contiguous burst instead of 4-byte stores spread over
 // up to 32 bins per warp instruction.  Output positions are identical to v1 (bit-exact, stable).
-template <bool FIRST>
-__global__ void __launch_bounds__(RS_THREADS)
+template <bool FIRST, bool PAY>
+__global__ void __launch_bounds__(RS_THREADS, PAY ? 3 : 4)
 rs_scatter2_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in, int64_t n, int shift,
                    int64_t nblocks, const int32_t* __restrict__ blockoff /*scanned [256][nblocks]*/,
-                   int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+                   int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
+                   const int32_t* __restrict__ pay_in, int32_t* __restrict__ pay_out) {
   __shared__ int32_t cnt[RS_WARPS][RS_BINS];
   __shared__ int32_t dstart[RS_BINS];   // tile-local start of digit d
   __shared__ int32_t gdelta[RS_BINS];   // global base of digit d for this tile - dstart[d]
   __shared__ int32_t skey[RS_TILE];
   __shared__ int32_t sval[RS_TILE];
+  __shared__ uint8_t sdig[PAY ? RS_TILE : 4];   // digit of the element at sorted slot j (payload pass only)
   __shared__ int32_t scan_sm[RS_THREADS / 32 + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -331,6 +387,7 @@ rs_scatter2_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restric
       const int32_t lp = dstart[d] + cnt[warp][d] + rank[r];
       skey[lp] = key[r];
       sval[lp] = FIRST ? (int32_t)k : vals_in[k];
+      if (PAY) sdig[lp] = (uint8_t)d;
     }
   }
   __syncthreads();
@@ -342,6 +399,115 @@ rs_scatter2_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restric
       const int32_t pos = gdelta[((uint32_t)kk >> shift) & 0xFF] + j;
       keys_out[pos] = kk;
       vals_out[pos] = sval[j];
+    }
+  }
+  if (!PAY) return;
+  // optional second payload (the CSR's column ids) rides along through the same slots: it is read at the element's
+  // CURRENT position -- in the first pass that is the original edge order, a coalesced stream -- so that no pass
+  // ever gathers it through the permutation (the old col = other[eid] gather moved 113 DRAM bytes per 4-byte id)
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    if (k < n) {
+      const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+      skey[dstart[d] + cnt[warp][d] + rank[r]] = pay_in[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int j = i * RS_THREADS + threadIdx.x;
+    if (j < tile_total) pay_out[gdelta[sdig[j]] + j] = skey[j];
+  }
+}
+
+// v3 of the scatter, CSR build only: the two values that follow a key -- its edge id and the column id -- travel as
+// ONE 8-byte slot (a single shared-memory exchange, 8-byte stores, no second round); the first pass creates the
+// slot from the element's position and a coalesced read of `other`, the last pass splits it into eid[] and col[].
+// 58 KB of dynamic shared memory, 3 CTAs per SM.
+constexpr size_t RS3_SMEM = (size_t)RS_WARPS * RS_BINS * 4 + 2 * RS_BINS * 4 + (size_t)RS_TILE * 4 + (size_t)RS_TILE * 8 + 64;
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(RS_THREADS, 3)
+rs_scatter3_kernel(const int32_t* __restrict__ keys_in, const int2* __restrict__ pay_in,
+                   const int32_t* __restrict__ other_first, int64_t n, int shift, int64_t nblocks,
+                   const int32_t* __restrict__ blockoff /*scanned [256][nblocks]*/, int32_t* __restrict__ keys_out,
+                   int2* __restrict__ pay_out, int32_t* __restrict__ eid_out, int32_t* __restrict__ col_out) {
+  extern __shared__ __align__(16) unsigned char rs3_raw[];
+  int2* spay = reinterpret_cast<int2*>(rs3_raw);                                  // [RS_TILE]
+  int32_t* skey = reinterpret_cast<int32_t*>(rs3_raw + (size_t)RS_TILE * 8);      // [RS_TILE]
+  int32_t(*cnt)[RS_BINS] = reinterpret_cast<int32_t(*)[RS_BINS]>(skey + RS_TILE); // [RS_WARPS][RS_BINS]
+  int32_t* dstart = &cnt[0][0] + RS_WARPS * RS_BINS;                              // [RS_BINS]
+  int32_t* gdelta = dstart + RS_BINS;                                             // [RS_BINS]
+  int32_t* scan_sm = gdelta + RS_BINS;                                            // [RS_THREADS/32 + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+
+  const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t wbase = tbase + (int64_t)warp * (32 * RS_ITEMS);
+  int32_t key[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    const bool valid = k < n;
+    key[r] = valid ? keys_in[k] : 0;
+    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    int32_t old = 0;
+    if (valid && lane == leader) {
+      old = cnt[warp][d];
+      cnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  int32_t tot = 0;
+  {
+    const int d = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const int32_t c = cnt[w][d];
+      cnt[w][d] = tot;
+      tot += c;
+    }
+  }
+  int32_t tile_total;
+  const int32_t ds = block_exclusive_scan<int32_t, RS_THREADS>(tot, &tile_total, scan_sm);
+  dstart[threadIdx.x] = ds;
+  gdelta[threadIdx.x] = blockoff[(int64_t)threadIdx.x * nblocks + blockIdx.x] - ds;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t k = wbase + r * 32 + lane;
+    if (k < n) {
+      const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+      const int32_t lp = dstart[d] + cnt[warp][d] + rank[r];
+      skey[lp] = key[r];
+      spay[lp] = FIRST ? make_int2((int32_t)k, other_first[k]) : pay_in[k];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int j = i * RS_THREADS + threadIdx.x;
+    if (j < tile_total) {
+      const int32_t kk = skey[j];
+      const int32_t pos = gdelta[((uint32_t)kk >> shift) & 0xFF] + j;
+      const int2 pv = spay[j];
+      keys_out[pos] = kk;
+      if (LAST) {
+        eid_out[pos] = pv.x;
+        col_out[pos] = pv.y;
+      } else {
+        pay_out[pos] = pv;
+      }
     }
   }
 }
@@ -361,11 +527,14 @@ rowptr_lower_bound_kernel(const int32_t* __restrict__ sorted, int64_t nnz, int64
   rowptr[r] = lo;
 }
 
-// 1 = first-round kernels (direct scatter, atomic degree histogram + scan), anything else = v2; read once.
+// RGBMP_BUILD_VARIANT (read once): 1 = first-round kernels (direct scatter, atomic degree histogram + scan,
+// col = other[eid] gather), 2 = shared-memory reorder with the column ids as a separate payload round,
+// default 3 = packed (eid, col) slots in the CSR sort.  All three are bit-identical; 1 and 2 stay for A/B timing.
 static int build_variant() {
   static const int v = [] {
     const char* e = getenv("RGBMP_BUILD_VARIANT");
-    return (e && e[0] == '1' && e[1] == 0) ? 1 : 2;
+    if (e && e[1] == 0 && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+    return 3;
   }();
   return v;
 }
@@ -491,30 +660,76 @@ __global__ void longrow_fill_kernel(const int64_t* __restrict__ rowptr, int64_t 
 // (original index of every sorted element) lands in vfinal.  kA/kB/vA: scratch of n int32 each.
 static int sort_pairs_i32(const int32_t* key, int64_t n, int bits, int32_t* kA, int32_t* kB, int32_t* vA,
                           int32_t* vfinal, int32_t* bh, int32_t* sc32, int64_t nb, cudaStream_t st,
-                          const int32_t** sorted_keys = nullptr) {
+                          const int32_t** sorted_keys = nullptr, const int32_t* pay = nullptr, int32_t* pA = nullptr,
+                          int32_t* pB = nullptr, int32_t* pay_final = nullptr) {
+  // pay (optional, v2 only): a second int32 per element that travels with the pair; the last pass writes pay_final
   const int passes = (bits + 7) / 8;
   const bool v2 = build_variant() != 1;
   const int32_t* kin = key;
   const int32_t* vin = nullptr;
+  const int32_t* pin = pay;
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
     int32_t* kout = (p & 1) ? kB : kA;
     int32_t* vout = (((passes - 1 - p) & 1) == 0) ? vfinal : vA;   // the LAST pass writes vfinal
+    int32_t* pout = !pay ? nullptr : (p == passes - 1) ? pay_final : ((p & 1) ? pB : pA);
     rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, n, shift, nb, bh);
     RGBMP_LAUNCH_CHECK("rs_hist_kernel");
     RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
     if (p == 0) {
-      if (v2) rs_scatter2_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+      if (v2 && pay) rs_scatter2_kernel<true, true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout, pin, pout);
+      else if (v2) rs_scatter2_kernel<true, false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout, nullptr, nullptr);
       else rs_scatter_kernel<true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
     } else {
-      if (v2) rs_scatter2_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
+      if (v2 && pay) rs_scatter2_kernel<false, true><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout, pin, pout);
+      else if (v2) rs_scatter2_kernel<false, false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout, nullptr, nullptr);
       else rs_scatter_kernel<false><<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, vin, n, shift, nb, bh, kout, vout);
     }
     RGBMP_LAUNCH_CHECK("rs_scatter_kernel");
     kin = kout;
     vin = vout;
+    pin = pout;
   }
   if (sorted_keys) *sorted_keys = kin;
+  return 0;
+}
+
+template <bool FIRST, bool LAST>
+static cudaError_t launch_scatter3(const int32_t* kin, const int2* pin, const int32_t* other, int64_t n, int shift, int64_t nb,
+                                   const int32_t* bh, int32_t* kout, int2* pout, int32_t* eid, int32_t* col, cudaStream_t st) {
+  auto fn = rs_scatter3_kernel<FIRST, LAST>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS3_SMEM);
+  if (e != cudaSuccess) return e;
+  fn<<<(unsigned)nb, RS_THREADS, RS3_SMEM, st>>>(kin, pin, other, n, shift, nb, bh, kout, pout, eid, col);
+  return cudaGetLastError();
+}
+
+// CSR sort with packed (eid, col) slots: sorts `key` (stable, low `bits` bits), writes eid[] and col[] = other[eid[]];
+// *sorted_keys = the sorted keys (in kA or kB).  pA/pB: n int2 each.
+static int sort_csr_packed(const int32_t* key, const int32_t* other, int64_t n, int bits, int32_t* kA, int32_t* kB,
+                           int2* pA, int2* pB, int32_t* eid, int32_t* col, int32_t* bh, int32_t* sc32, int64_t nb,
+                           cudaStream_t st, const int32_t** sorted_keys) {
+  const int passes = (bits + 7) / 8;
+  const int32_t* kin = key;
+  const int2* pin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    const bool first = p == 0, last = p == passes - 1;
+    int32_t* kout = (p & 1) ? kB : kA;
+    int2* pout = (p & 1) ? pB : pA;
+    rs_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, st>>>(kin, n, shift, nb, bh);
+    RGBMP_LAUNCH_CHECK("rs_hist_kernel");
+    RGBMP_CUDA(exclusive_scan<int32_t>(bh, (int64_t)RS_BINS * nb, sc32, st));
+    cudaError_t e;
+    if (first && last) e = launch_scatter3<true, true>(kin, pin, other, n, shift, nb, bh, kout, pout, eid, col, st);
+    else if (first) e = launch_scatter3<true, false>(kin, pin, other, n, shift, nb, bh, kout, pout, eid, col, st);
+    else if (last) e = launch_scatter3<false, true>(kin, pin, other, n, shift, nb, bh, kout, pout, eid, col, st);
+    else e = launch_scatter3<false, false>(kin, pin, other, n, shift, nb, bh, kout, pout, eid, col, st);
+    if (e != cudaSuccess) return cuda_fail(e, "rs_scatter3_kernel");
+    kin = kout;
+    pin = pout;
+  }
+  *sorted_keys = kin;
   return 0;
 }
 
@@ -633,7 +848,8 @@ int rgbmp_edge_edit(const int64_t* src, const int64_t* dst, int64_t E, int64_t N
     RGBMP_LAUNCH_CHECK("ee_count_kernel");
     ee_save_last_kernel<<<1, 32, 0, st>>>(blockcnt, nb, last);
     RGBMP_CUDA(exclusive_scan<int32_t>(blockcnt, nb, scanws, st));
-    ee_write_kernel<<<(unsigned)nb, EE_THREADS, 0, st>>>(src, dst, E, filter, blockcnt, e_src, e_dst);
+    if (build_variant() != 1) ee_write2_kernel<<<(unsigned)nb, EE_THREADS, 0, st>>>(src, dst, E, filter, blockcnt, e_src, e_dst);
+    else ee_write_kernel<<<(unsigned)nb, EE_THREADS, 0, st>>>(src, dst, E, filter, blockcnt, e_src, e_dst);
     RGBMP_LAUNCH_CHECK("ee_write_kernel");
   } else {
     RGBMP_CUDA(cudaMemsetAsync(last, 0, sizeof(int32_t), st));
@@ -650,7 +866,7 @@ size_t rgbmp_csr_build_workspace_bytes(int64_t nnz, int64_t N) {
   const size_t n = (size_t)(nnz > 0 ? nnz : 1);
   const size_t nb = (size_t)ceil_div((int64_t)n, RS_TILE);
   size_t b = 0;
-  b += 3 * align_up(n * sizeof(int32_t), 256);                                    // keys A/B, vals A
+  b += 2 * align_up(n * sizeof(int32_t), 256) + 2 * align_up(2 * n * sizeof(int32_t), 256);   // keys A/B, (eid, col) slots A/B
   b += align_up(RS_BINS * nb * sizeof(int32_t), 256);                              // block histograms
   b += align_up(scan_ws_elems((int64_t)(RS_BINS * nb)) * sizeof(int32_t), 256);    // scan scratch (i32)
   b += align_up(scan_ws_elems(N + 1) * sizeof(int64_t), 256);                      // scan scratch (i64)
@@ -673,7 +889,9 @@ int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64
   Carver cv(ws, ws_bytes);
   int32_t* kA = cv.take<int32_t>(n);
   int32_t* kB = cv.take<int32_t>(n);
-  int32_t* vA = cv.take<int32_t>(n);
+  int32_t* vA = cv.take<int32_t>(2 * n);   // variants 1/2: vals A in the first half, payload A in the second; variant 3: packed slots A
+  int32_t* pA = vA + n;
+  int32_t* pB = cv.take<int32_t>(2 * n);   // variant 2: payload B; variant 3: packed slots B
   int32_t* bh = cv.take<int32_t>((size_t)RS_BINS * nb);
   int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
   int64_t* sc64 = cv.take<int64_t>(scan_ws_elems(N + 1));
@@ -693,12 +911,17 @@ int rgbmp_csr_build(const int32_t* key, const int32_t* other, int64_t nnz, int64
   int bits = 1;
   while (bits < 31 && (1ll << bits) < N) ++bits;
   const int32_t* sorted = nullptr;
-  const int rc_sort = sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st, &sorted);
-  if (rc_sort) return rc_sort;
-  if (v2) {   // rowptr straight from the sorted keys
+  if (v2) {   // the column ids ride through the sort; rowptr straight from the sorted keys
+    const int rc_sort = build_variant() == 2
+        ? sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st, &sorted, other, pA, pB, col)
+        : sort_csr_packed(key, other, nnz, bits, kA, kB, (int2*)vA, (int2*)pB, eid, col, bh, sc32, nb, st, &sorted);
+    if (rc_sort) return rc_sort;
     rowptr_lower_bound_kernel<<<(unsigned)ceil_div(N + 1, 256), 256, 0, st>>>(sorted, nnz, N, rowptr);
     RGBMP_LAUNCH_CHECK("rowptr_lower_bound_kernel");
+    return 0;
   }
+  const int rc_sort = sort_pairs_i32(key, nnz, bits, kA, kB, vA, eid, bh, sc32, nb, st, &sorted);
+  if (rc_sort) return rc_sort;
   gather_i32_kernel<<<kSMs * 8, 256, 0, st>>>(other, eid, nnz, col);
   RGBMP_LAUNCH_CHECK("gather_i32_kernel");
   return 0;

@@ -151,9 +151,11 @@ def test_coalesce_rejects_out_of_range_ids():
         U.to_undirected(ei, 6)
 
 
-def test_first_round_build_kernels_are_still_bit_exact():
-    """RGBMP_BUILD_VARIANT=1 selects the first-round kernels (direct scatter, atomic degree histogram);
-    the variant is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_earlier_build_variants_are_still_bit_exact(variant):
+    """RGBMP_BUILD_VARIANT=1 selects the first-round kernels (direct scatter, atomic degree histogram, col gather),
+    2 the shared-memory reorder with a separate column payload round (default: packed slots); the variant is read
+    once per process, hence the subprocess."""
     import os
     import subprocess
     import sys
@@ -166,7 +168,7 @@ def test_first_round_build_kernels_are_still_bit_exact():
         "    ei, n = CASES[case]()\n"
         "    T.check_graph(ei, n, 2)\n"
         "print('variant1 ok')\n" % (root, os.path.join(root, "tests")))
-    env = dict(os.environ, RGBMP_BUILD_VARIANT="1")
+    env = dict(os.environ, RGBMP_BUILD_VARIANT=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "variant1 ok" in r.stdout, r.stdout + r.stderr
 
