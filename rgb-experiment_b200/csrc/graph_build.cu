@@ -253,10 +253,16 @@ rs_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int shift, int64_t n
   h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  int32_t kk[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {                 // all loads in flight before the first shared-memory atomic
+    const int64_t k = base + (int64_t)i * RS_THREADS + threadIdx.x;
+    kk[i] = (k < n) ? __ldcs(keys + k) : 0;
+  }
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
     const int64_t k = base + (int64_t)i * RS_THREADS + threadIdx.x;
-    if (k < n) atomicAdd(&h[((uint32_t)keys[k] >> shift) & 0xFF], 1);
+    if (k < n) atomicAdd(&h[((uint32_t)kk[i] >> shift) & 0xFF], 1);
   }
   __syncthreads();
   blockhist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
@@ -321,6 +327,21 @@ rs_scatter_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restrict
   }
 }
 
+// Lanes of the warp that hold the same 8-bit digit (and the same validity) as the caller.  Eight ballots + LOP3s on
+// the ALU pipe instead of one match.any: the ncu profile of the scatter (profiles/r01_build_scatter3_ncu_full.txt)
+// showed the ADU pipe, where MATCH executes, 57-60 % busy at 37 % occupancy -- the kernel's limiter.
+__device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool valid) {
+  const uint32_t vb = __ballot_sync(0xffffffffu, valid);
+  uint32_t peers = valid ? vb : ~vb;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
 // v2 of the scatter: the tile is first reordered by digit in shared memory (same stable ranks), then written out
 // by consecutive threads -- every (tile, digit) run becomes one contiguous burst instead of 4-byte stores spread over
 // up to 32 bins per warp instruction.  Output positions are identical to v1 (bit-exact, stable).
@@ -351,8 +372,8 @@ rs_scatter2_kernel(const int32_t* __restrict__ keys_in, const int32_t* __restric
     const int64_t k = wbase + r * 32 + lane;
     const bool valid = k < n;
     key[r] = valid ? keys_in[k] : 0;
-    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+    const uint32_t peers = digit_peers(d, valid);
     const int leader = __ffs(peers) - 1;
     int32_t old = 0;
     if (valid && lane == leader) {
@@ -455,8 +476,8 @@ rs_scatter3_kernel(const int32_t* __restrict__ keys_in, const int2* __restrict__
     const int64_t k = wbase + r * 32 + lane;
     const bool valid = k < n;
     key[r] = valid ? keys_in[k] : 0;
-    const uint32_t d = valid ? (((uint32_t)key[r] >> shift) & 0xFF) : 0xFFFFFFFFu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t d = ((uint32_t)key[r] >> shift) & 0xFF;
+    const uint32_t peers = digit_peers(d, valid);
     const int leader = __ffs(peers) - 1;
     int32_t old = 0;
     if (valid && lane == leader) {

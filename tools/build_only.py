@@ -45,7 +45,7 @@ def main():
     algo = E * 16 * 2 + nnz * 8 + 2 * (nnz * (passes * 20 + 12) + (N + 1) * 8)
     best = min(ts)
     print(json.dumps({"config": "graph_build(edit+CSR+transpose CSR)", "workload": args.workload, "N": N, "E": E, "nnz": nnz,
-                      "variant": os.environ.get("RGBMP_BUILD_VARIANT", "2"), "ms": round(best, 3),
+                      "variant": os.environ.get("RGBMP_BUILD_VARIANT", "3"), "ms": round(best, 3),
                       "edit_plus_fwd_ms": round(parts[0], 3), "transpose_ms": round(parts[1], 3),
                       "Medges_per_s": round(E / best / 1e3, 1), "algorithmic_GB": round(algo / 1e9, 2),
                       "algorithmic_GBps": round(algo / best / 1e6, 1)}), flush=True)
