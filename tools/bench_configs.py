@@ -163,7 +163,41 @@ def main():
             B = g.nnz * (H * C * 4 + H * 4 + 4) + N * H * C * 4 + 2 * N * H * 4
             out(config=f"C3 GAT layer H={H} C={C} reddit-shaped", nnz=g.nnz, fwd_ms=fwd, fwd_gteps=g.nnz / fwd / 1e6,
                 fwd_GBps=B / fwd / 1e6, frac_of_measured_hbm=B / fwd / 1e6 / PEAK, fwd_bwd_ms=fbm)
-        del sg, g
+        # the whole 2-layer model of models/gat.py:18-31 (GATConv 602 -> 8x8, BatchNorm, GATConv 64 -> 41 with one head) for one
+        # reference epoch (1 train fwd+bwd+Adam, 2 eval fwd) -- the configuration that runs the reference out of memory
+        del sg
+        sgx = S.make_named("reddit", device=dev)
+
+        class GAT(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.c1 = L.GATConv(sgx.x.size(1), 8, 8)
+                self.bn = nn.BatchNorm1d(64)
+                self.c2 = L.GATConv(64, sgx.num_classes, 1, concat=False)
+
+            def forward(self, x, ei):
+                return F.log_softmax(self.c2(self.bn(self.c1(x, ei)), ei), 1)
+
+        m = GAT().to(dev)
+        opt = torch.optim.Adam(m.parameters(), lr=0.01)
+        tr = torch.arange(N, device=dev) % 10 < 6
+
+        def epoch():
+            m.train()
+            opt.zero_grad()
+            F.nll_loss(m(sgx.x, sgx.edge_index)[tr], sgx.y[tr]).backward()
+            opt.step()
+            m.eval()
+            with torch.no_grad():
+                m(sgx.x, sgx.edge_index)
+                m(sgx.x, sgx.edge_index)
+
+        torch.cuda.reset_peak_memory_stats()
+        ms = ev_ms(epoch, 5, 2)
+        out(config="C3 GAT 2-layer (8x8 heads, then 1x41) reddit-shaped, full-batch epoch", epoch_ms=ms,
+            peak_mem_GiB=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+            note="1 train fwd+bwd+Adam + 2 eval fwd; PyG materialises [nnz,8,8] = 29.4 GB per layer-forward here (SURVEY 8a a4)")
+        del sgx, g, m
 
     if "c4" in only:
         sg = S.make_named("products", device=dev, features=False)
