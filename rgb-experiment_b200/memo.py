@@ -128,7 +128,8 @@ def cached(owner, static_key: tuple, tensors: Sequence[torch.Tensor], work: floa
             _gen, _in_train = _gen + 1, True
     else:
         _in_train = False
-    if torch.is_grad_enabled() or _budget_bytes <= 0 or work < MIN_WORK or \
+    # inference_mode tensors carry no version counter (the in-place guard below needs it): not memoised
+    if torch.is_grad_enabled() or torch.is_inference_mode_enabled() or _budget_bytes <= 0 or work < MIN_WORK or \
             2 * sum(t.numel() * t.element_size() for t in tensors) > _budget_bytes:
         stats["skipped"] += 1
         return fn()

@@ -148,3 +148,13 @@ def test_a_training_forward_makes_the_previous_generation_droppable():
         assert len(M._store) == min(epoch, 1) + 2       # this and the previous epoch's x + raw, nothing older
     # per epoch: x misses once and hits once; raw misses only in the first epoch
     assert M.stats["misses"] == 5 + 1 and M.stats["hits"] == 5 + 9 and M.stats["stale_dropped"] == 3
+
+
+def test_inference_mode_is_not_memoised():
+    g, calls = _Owner(), []
+    f = _op(calls)
+    with torch.inference_mode():
+        x = torch.randn(10, 3)
+        M.cached(g, ("op",), (x,), BIG, lambda: f(x))
+        M.cached(g, ("op",), (x,), BIG, lambda: f(x))
+    assert len(calls) == 2 and M.stats["hits"] == 0 and M.stats["misses"] == 0
