@@ -124,6 +124,28 @@ def cpu_hop(s, d, w, z, n_sub, alpha=ALPHA):
     return out + alpha * z[:n_sub]
 
 
+def cpu_strong_baseline(s, d, w, z, n_sub, budget_s=10.0, alpha=ALPHA):
+    """the same hop as one torch.sparse CSR product A @ z on the host cores -- no [nnz, F] message
+    tensor, the strongest CPU form available in this image.  Reported beside the literal PyG form, never instead of it."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        perm = torch.argsort(d, stable=True)
+        crow = torch.zeros(n_sub + 1, dtype=torch.int64)
+        crow[1:] = torch.cumsum(torch.bincount(d, minlength=n_sub), 0)
+        A = torch.sparse_csr_tensor(crow, s[perm], w[perm], size=(n_sub, z.size(0)))
+        best, hops, t_all = None, 0, time.perf_counter()
+        while hops < 6 and (hops < 2 or time.perf_counter() - t_all < budget_s):
+            t0 = time.perf_counter()
+            out = (A @ z) * (1 - alpha) + alpha * z[:n_sub]
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            hops += 1
+    del out
+    return {"value": s.numel() / best / 1e9, "unit": "GTEPS", "kind": "torch.sparse CSR A @ z on the same sample and weights",
+            "best_of": hops}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -147,7 +169,8 @@ def run_reference(args, rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(N_full, nnz_full, F_CLASSES), "hops_per_step": 1, "nnz": nnz_full,
                        "parallelism": f"{cores} host threads", "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample,
+                             "strong": cpu_strong_baseline(s, d, w, z, n_sub)},
             "e2e": {"value": val, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -376,7 +399,8 @@ def main():
         cpu_baseline = {"value": s.numel() / best / 1e9, "unit": "GTEPS", "cores": torch.get_num_threads(),
                         "kind": "port",
                         "sample": f"best of {hops} single hops over the {s.numel()} edges whose target is in the first "
-                                  f"{int(CPU_SAMPLE_FRACTION * 100)}% of nodes; literal index_select->mul->scatter_add_ fp32"}
+                                  f"{int(CPU_SAMPLE_FRACTION * 100)}% of nodes; literal index_select->mul->scatter_add_ fp32",
+                        "strong": cpu_strong_baseline(s, d, w, z, n_sub)}
 
     line = {"metric": "appnp_propagate_gteps", "value": gteps, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
