@@ -1,6 +1,7 @@
 """CPU oracle for the message-passing hot path -- TEST INFRASTRUCTURE ONLY.
 
-This package is a pure-torch / numpy restatement of the arithmetic that the
+This package is a pure-torch restatement (pyg_restated.py, layers.py) plus a plain-C one (csrc/rgb_oracle.c,
+scalar loops in edge order, bound by c_oracle.py; bit-identical to the torch form) of the arithmetic that the
 reference (PolarisRisingWar/rgb-experiment) delegates to torch_geometric /
 torch_scatter / torch_sparse (none of which exist in this image or on the GPU
 box).  It is the checker the CUDA path
