@@ -149,6 +149,12 @@ def cpu_strong_baseline(s, d, w, z, n_sub, budget_s=10.0, alpha=ALPHA):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the other ranks have already left, so rank 0 takes every
+    # host core it is allowed to run on (the same thread count a plain `python bench.py --impl reference` gets)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     sg = make_workload(dev)
     N_full, nnz_full = sg.num_nodes, sg.edge_index.size(1) + sg.num_nodes      # the generator emits no self loops
