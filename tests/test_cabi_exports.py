@@ -62,6 +62,12 @@ def test_product_path_has_no_cpu_fallback():
     src = open(os.path.join(ROOT, "rgb-experiment_b200", "ops.py")).read() + \
         open(os.path.join(ROOT, "rgb-experiment_b200", "graph.py")).read()
     assert "oracle" not in src                      # the product never imports the checker
+    pkg = os.path.join(ROOT, "rgb-experiment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
 
 
 def test_shim_exposes_every_name_the_reference_imports():
