@@ -9,7 +9,9 @@ layers (stable across epochs).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
+import weakref
 from collections import OrderedDict
 from typing import Optional
 
@@ -197,6 +199,7 @@ class Graph:
         self._bwd: Optional[CSR] = None
         self._lock = threading.Lock()
         self._vals = {}
+        self._perm_memo = {}
 
     # transpose CSR: rows = sources j, col = targets i (built on first backward)
     @property
@@ -248,13 +251,23 @@ class Graph:
         return v
 
     def to_csr_order(self, edge_vals: torch.Tensor, transpose: bool = False) -> torch.Tensor:
-        """edge-ordered [nnz] or [nnz,H] float32 -> CSR order of the chosen orientation."""
+        """edge-ordered [nnz] or [nnz,H] float32 -> CSR order of the chosen orientation.  The last permuted
+        tensor of each orientation is remembered on the identity (weakref + _version) of its source: DAGNN's Prop
+        passes the SAME `norm` to all K hops of a forward (dagnn.py:41-46), so K-1 of K permutations are hits."""
+        last = self._perm_memo.get(transpose)
+        if last is not None and last[0]() is edge_vals and last[1] == edge_vals._version and \
+                not (edge_vals.requires_grad and torch.is_grad_enabled()):
+            return last[2]
         csr = self.bwd if transpose else self.fwd
-        ev = edge_vals.contiguous().to(torch.float32)
+        ev = edge_vals.detach().contiguous().to(torch.float32)
         H = 1 if ev.dim() == 1 else ev.size(1)
         out = torch.empty_like(ev)
         check(lib().rgbmp_edge_permute(ptr(ev), ptr(csr.eid), self.nnz, H, 0, ptr(out), self.device.index,
                                        stream_of(self.device)), "edge_permute")
+        try:
+            self._perm_memo[transpose] = (weakref.ref(edge_vals), edge_vals._version, out)
+        except TypeError:
+            pass
         return out
 
     def to_edge_order(self, csr_vals: torch.Tensor, transpose: bool = False) -> torch.Tensor:
@@ -269,29 +282,81 @@ class Graph:
 
 # --------------------------------------------------------------------------------------------
 # cache keyed on the identity of the edge_index tensor that reaches the layers
+#
+# An entry lives exactly as long as the edge_index TENSOR it was built from: a weakref callback drops
+# it when that tensor dies (so the allocator can never hand its address to a different edge list that
+# would alias the key), nothing here keeps the caller's tensor alive, and the total is capped in BYTES
+# (RGBMP_GRAPH_CACHE_MB, default 32768: a products-sized Graph with both orientations, weights and hot
+# tags is ~5 GB).  On a CUDA out-of-memory error the caches are emptied and the call is retried once
+# (`oom_retry`) -- the reference's sweeps treat any RuntimeError as "model too big"
+# (examples/all_dataset_baseline.py:65-66), so memory pinned by earlier datasets must not cause one.
 # --------------------------------------------------------------------------------------------
-_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
-_CACHE_LOCK = threading.Lock()
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()      # key -> (Graph, weakref to the keyed tensor, nbytes)
+_CACHE_LOCK = threading.RLock()
 _CACHE_MAX = 16
-stats = {"hits": 0, "builds": 0}
+_CACHE_MAX_BYTES = int(float(os.environ.get("RGBMP_GRAPH_CACHE_MB", "32768")) * (1 << 20))
+stats = {"hits": 0, "builds": 0, "evicted": 0, "oom_retries": 0}
 
 
-def get_graph(edge_index: torch.Tensor, num_nodes: int, loop_mode: int) -> Graph:
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
-           int(num_nodes), int(loop_mode), str(edge_index.device))
+def _graph_key(edge_index: torch.Tensor, num_nodes: int, loop_mode: int, reverse: bool) -> tuple:
+    return (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
+            int(num_nodes), int(loop_mode), str(edge_index.device), bool(reverse))
+
+
+def _drop(key) -> None:
+    with _CACHE_LOCK:
+        _CACHE.pop(key, None)
+
+
+def cache_bytes() -> int:
+    with _CACHE_LOCK:
+        return sum(v[2] for v in _CACHE.values())
+
+
+def _build_nbytes(g: "Graph") -> int:
+    """Bytes a freshly built Graph holds, plus what its lazily built parts will add (transpose CSR, weights in
+    both orientations, one hot-tagged column copy each): the cap is about what an entry may grow to."""
+    nnz, n = g.nnz, g.N
+    return 2 * 4 * nnz + 2 * (8 * (n + 1) + 8 * nnz + 4 * n) + 2 * 4 * nnz + 2 * 4 * nnz
+
+
+def oom_retry(fn):
+    """Run fn(); on a CUDA OOM drop every cached graph and memoised result, return the blocks to the driver
+    and try once more."""
+    try:
+        return fn()
+    except torch.cuda.OutOfMemoryError:
+        stats["oom_retries"] += 1
+        clear_cache()
+        from . import memo
+        memo.clear()
+        from .shim import utils as _u
+        _u.clear_memo()
+        torch.cuda.empty_cache()
+        return fn()
+
+
+def get_graph(edge_index: torch.Tensor, num_nodes: int, loop_mode: int, reverse: bool = False) -> Graph:
+    """Cached Graph of `edge_index` (reverse=True: of edge_index.flip(0), keyed on the ORIGINAL tensor so that
+    callers which need the reversed orientation -- PTA, SURVEY B7 -- do not mint a new cache key per call)."""
+    key = _graph_key(edge_index, num_nodes, loop_mode, reverse)
     with _CACHE_LOCK:
         hit = _CACHE.get(key)
-        if hit is not None:
+        if hit is not None and hit[1]() is edge_index:
             _CACHE.move_to_end(key)
             stats["hits"] += 1
             return hit[0]
-    g = Graph(edge_index, num_nodes, loop_mode)
+    src = edge_index.flip(0).contiguous() if reverse else edge_index
+    g = oom_retry(lambda: Graph(src, num_nodes, loop_mode))
+    del src
+    nbytes = _build_nbytes(g)
     with _CACHE_LOCK:
-        # keep a reference to the tensor so that its storage (and therefore the key) stays unique
-        _CACHE[key] = (g, edge_index)
+        _CACHE[key] = (g, weakref.ref(edge_index, lambda _r, k=key: _drop(k)), nbytes)
+        _CACHE.move_to_end(key)
         stats["builds"] += 1
-        while len(_CACHE) > _CACHE_MAX:
+        while len(_CACHE) > 1 and (len(_CACHE) > _CACHE_MAX or sum(v[2] for v in _CACHE.values()) > _CACHE_MAX_BYTES):
             _CACHE.popitem(last=False)
+            stats["evicted"] += 1
     return g
 
 

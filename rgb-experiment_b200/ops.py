@@ -13,7 +13,7 @@ import torch
 
 from . import _lib, memo
 from ._lib import Epilogue, check, dtype_code, lib, ptr, stream_of
-from .graph import CSR, Graph, NORM_COUNT, NORM_INV_SQRT
+from .graph import CSR, Graph, NORM_COUNT, NORM_INV_SQRT, oom_retry
 
 RESET_NONE, RESET_BEFORE_TELEPORT, RESET_AFTER_CLAMP = 0, 1, 2
 
@@ -84,10 +84,16 @@ def _graph_ref(csr, row_bytes: int, hot: bool = True):
     return csr.ref
 
 
-def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, ep: Optional[Epilogue] = None,
-             keep=(), tune: int = 0, out: Optional[torch.Tensor] = None, hot: bool = True,
-             store_local: bool = True) -> Optional[torch.Tensor]:
-    """y[i] = epilogue(sum_k val[k] * x[col[k]]).  `keep` holds tensors referenced by `ep`.
+def spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, **kw) -> Optional[torch.Tensor]:
+    """y[i] = epilogue(sum_k val[k] * x[col[k]]); see _spmm_raw.  A CUDA OOM empties the graph / memo caches and
+    retries once (graph.oom_retry)."""
+    return oom_retry(lambda: _spmm_raw(csr, x, val, **kw))
+
+
+def _spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, ep: Optional[Epilogue] = None,
+              keep=(), tune: int = 0, out: Optional[torch.Tensor] = None, hot: bool = True,
+              store_local: bool = True) -> Optional[torch.Tensor]:
+    """`keep` holds tensors referenced by `ep`.
     hot=True lets feature matrices beyond the L2 budget use the hot-tagged column ids (graph.CSR.hot_ref)."""
     xb, ldx = as_rows(x)
     F = x.size(1)
@@ -116,9 +122,13 @@ def row_scale(x: torch.Tensor, scale: torch.Tensor, divide: bool = False) -> tor
     return y
 
 
-def khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilogue] = None, keep=(),
-             hops: bool = False, tune: int = 0, hot: bool = True):
+def khop_raw(csr: CSR, x0: torch.Tensor, K: int, **kw):
     """K fused hops.  Returns the final iterate, or (final, [K, N, F] hop outputs) when hops=True."""
+    return oom_retry(lambda: _khop_raw(csr, x0, K, **kw))
+
+
+def _khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilogue] = None, keep=(),
+              hops: bool = False, tune: int = 0, hot: bool = True):
     xb, ldx = as_rows(x0)
     N, F = x0.shape
     dev, dt = x0.device, x0.dtype
@@ -209,15 +219,23 @@ def propagate_weighted(x, w, graph: Graph):
 # ------------------------------------------------------------------------------------------
 # K-hop families
 # ------------------------------------------------------------------------------------------
-def _appnp_khop(csr: CSR, graph: Graph, x: torch.Tensor, K: int, alpha: float, transpose: bool, fold: bool):
-    xb, ldx = as_rows(x)
+FOLD_KHOP = True     # K-hop families apply D^-1/2 (A+I) D^-1/2 as row scalings around an unweighted sum (no per-edge
+                     # weight stream, 4 B/edge less and adds instead of FMAs); False: per-edge gcn_norm weights as PyG multiplies them
+
+
+def _khop_gcn(csr: CSR, graph: Graph, x0b: torch.Tensor, K: int, transpose: bool, fold: bool, **epkw):
+    """K hops of z <- epilogue(A_hat z) on the chosen orientation.  fold: the iterate travels pre-scaled
+    (u = D^-1/2 z, what the next hop gathers) and the epilogue scales the row sum by D^-1/2 again; the
+    in-degree vector serves both orientations (A_hat^T = D^-1/2 A^T D^-1/2 with the same D)."""
     if fold:
         d = graph.dinv()
-        u0 = row_scale(xb, d)
-        ep = make_epilogue(row_scale=d, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx, out2_scale=d)
-        return khop_raw(csr, u0, K, ep=ep, keep=(d, xb))
-    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
-    return khop_raw(csr, xb, K, val=graph.gcn_val(transpose), ep=ep, keep=(xb,))
+        return khop_raw(csr, row_scale(x0b, d), K, ep=make_epilogue(row_scale=d, out2_scale=d, **epkw))
+    return khop_raw(csr, x0b, K, val=graph.gcn_val(transpose), ep=make_epilogue(**epkw))
+
+
+def _appnp_khop(csr: CSR, graph: Graph, x: torch.Tensor, K: int, alpha: float, transpose: bool, fold: bool):
+    xb, ldx = as_rows(x)
+    return _khop_gcn(csr, graph, xb, K, transpose, fold, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
 
 
 class _APPNP(torch.autograd.Function):
@@ -236,10 +254,10 @@ class _APPNP(torch.autograd.Function):
         return _appnp_khop(g.bwd, g, dz, ctx.K, ctx.alpha, True, ctx.fold), None, None, None, None
 
 
-def appnp(x, graph: Graph, K: int, alpha: float, fold: bool = False):
+def appnp(x, graph: Graph, K: int, alpha: float, fold: Optional[bool] = None):
     if K == 0:
         return x
-    K, alpha, fold = int(K), float(alpha), bool(fold)
+    K, alpha, fold = int(K), float(alpha), bool(FOLD_KHOP if fold is None else fold)
     return memo.cached(graph, ("appnp", K, alpha, fold), (x,), K * _work(graph, x),
                        lambda: _APPNP.apply(x, graph, K, alpha, fold))
 
@@ -248,21 +266,22 @@ class _PowerHops(torch.autograd.Function):
     """x <- A_hat^K x (A9 SGConv, sgc.py:9-10)."""
 
     @staticmethod
-    def forward(ctx, x, graph: Graph, K: int):
-        ctx.graph, ctx.K = graph, K
-        return khop_raw(graph.fwd, x, K, val=graph.gcn_val(False))
+    def forward(ctx, x, graph: Graph, K: int, fold: bool):
+        ctx.graph, ctx.K, ctx.fold = graph, K, fold
+        return _khop_gcn(graph.fwd, graph, as_rows(x)[0], K, False, fold)
 
     @staticmethod
     def backward(ctx, dy):
         g = ctx.graph
-        return khop_raw(g.bwd, dy, ctx.K, val=g.gcn_val(True)), None, None
+        return _khop_gcn(g.bwd, g, as_rows(dy)[0], ctx.K, True, ctx.fold), None, None, None
 
 
-def gcn_power(x, graph: Graph, K: int):
+def gcn_power(x, graph: Graph, K: int, fold: Optional[bool] = None):
     if K == 0:
         return x
-    return memo.cached(graph, ("gcn_power", int(K)), (x,), K * _work(graph, x),
-                       lambda: _PowerHops.apply(x, graph, int(K)))
+    fold = bool(FOLD_KHOP if fold is None else fold)
+    return memo.cached(graph, ("gcn_power", int(K), fold), (x,), K * _work(graph, x),
+                       lambda: _PowerHops.apply(x, graph, int(K), fold))
 
 
 def dagnn_hops(x: torch.Tensor, graph: Graph, K: int) -> torch.Tensor:
@@ -272,7 +291,7 @@ def dagnn_hops(x: torch.Tensor, graph: Graph, K: int) -> torch.Tensor:
 
 
 def label_propagation(graph: Graph, out0: torch.Tensor, num_layers: int, alpha: float, *,
-                      clamp=(0.0, 1.0), reset_mask=None, reset_val=None) -> torch.Tensor:
+                      clamp=(0.0, 1.0), reset_mask=None, reset_val=None, fold: Optional[bool] = None) -> torch.Tensor:
     """A15 LP core: res=(1-a)*out0; L x { out = a * A_hat out + res; post_step }.
     post_step = clamp(lo,hi) (default / autoscale) or `out[mask] = reset_val[mask]` (fixed scale).
     `graph` must be built with LOOP_NONE (gcn_norm(add_self_loops=False))."""
@@ -287,8 +306,8 @@ def label_propagation(graph: Graph, out0: torch.Tensor, num_layers: int, alpha: 
         kw = dict(reset_mask=m, reset_val=rv, ld_reset=ldr, reset_when=RESET_AFTER_CLAMP)
         keep += [m, rv]
         clamp = None
-    ep = make_epilogue(a=alpha, b=1.0 - alpha, T=xb, ldt=ldx, clamp=clamp, **kw)
-    return khop_raw(graph.fwd, xb, num_layers, val=graph.gcn_val(False), ep=ep, keep=keep)
+    return _khop_gcn(graph.fwd, graph, xb, num_layers, False, bool(FOLD_KHOP if fold is None else fold),
+                     a=alpha, b=1.0 - alpha, T=xb, ldt=ldx, clamp=clamp, **kw)
 
 
 # ------------------------------------------------------------------------------------------
@@ -299,14 +318,13 @@ def label_propagation(graph: Graph, out0: torch.Tensor, num_layers: int, alpha: 
 # ------------------------------------------------------------------------------------------
 def pta_graph(edge_index: torch.Tensor, num_nodes: int) -> Graph:
     from .graph import LOOP_ADD, get_graph
-    return get_graph(edge_index.flip(0).contiguous(), num_nodes, LOOP_ADD)
+    return get_graph(edge_index, num_nodes, LOOP_ADD, reverse=True)
 
 
 def pta_inference(h: torch.Tensor, graph: Graph, K: int, alpha: float) -> torch.Tensor:
     y0 = torch.softmax(h, dim=-1)
     xb, ldx = as_rows(y0)
-    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
-    return khop_raw(graph.fwd, xb, K, val=graph.gcn_val(False), ep=ep, keep=(xb,))
+    return _khop_gcn(graph.fwd, graph, xb, K, False, FOLD_KHOP, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
 
 
 def pta_label_propagation(graph: Graph, labels: torch.Tensor, idx: torch.Tensor, K: int, alpha: float):
@@ -318,9 +336,8 @@ def pta_label_propagation(graph: Graph, labels: torch.Tensor, idx: torch.Tensor,
     mask[idx] = 1
     xb, ldx = as_rows(y0)
     # y <- A y ; y[idx] <- onehot[idx] (= y0[idx]) ; y <- (1-a) y + a y0
-    ep = make_epilogue(a=1.0 - alpha, b=alpha, T=xb, ldt=ldx, reset_mask=mask, reset_val=xb, ld_reset=ldx,
-                       reset_when=RESET_BEFORE_TELEPORT)
-    return khop_raw(graph.fwd, xb, K, val=graph.gcn_val(False), ep=ep, keep=(xb, mask))
+    return _khop_gcn(graph.fwd, graph, xb, K, False, FOLD_KHOP, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx, reset_mask=mask,
+                     reset_val=xb, ld_reset=ldx, reset_when=RESET_BEFORE_TELEPORT)
 
 
 # ------------------------------------------------------------------------------------------

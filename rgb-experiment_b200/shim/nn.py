@@ -316,7 +316,8 @@ class APPNP(MessagePassing):
     """A8 (models/appnp_stack.py:22): fused K-hop propagation with the teleport term in the
     SpMM epilogue; backward = the same recursion on the transpose graph."""
 
-    fold_norm = False      # True: fold D^-1/2 into row scaling (no per-edge weight read)
+    fold_norm = None       # None: ops.FOLD_KHOP (folded D^-1/2 row scalings, the measured path of bench.py);
+                           # False: per-edge gcn_norm weights exactly as PyG multiplies them
 
     def __init__(self, K, alpha, dropout=0.0, cached=False, add_self_loops=True, normalize=True, **kwargs):
         kwargs.setdefault("aggr", "add")

@@ -39,7 +39,7 @@ class _CudaBackend:
         _lib.require_cuda(edge_index, "edge_index")
         if add_identity:
             return ops.pta_graph(edge_index, num_nodes)
-        return get_graph(edge_index.flip(0).contiguous(), num_nodes, LOOP_NONE)
+        return get_graph(edge_index, num_nodes, LOOP_NONE, reverse=True)
 
     @staticmethod
     def label_propagation(graph, labels, idx, K, alpha):

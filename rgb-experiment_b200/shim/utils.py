@@ -8,6 +8,7 @@ keeps hitting."""
 from __future__ import annotations
 
 import threading
+import weakref
 from collections import OrderedDict
 from typing import Optional
 
@@ -17,9 +18,15 @@ from .. import _lib
 from ..graph import (LOOP_ADD, LOOP_ADD_REMAINING, LOOP_NONE, LOOP_REMOVE_THEN_ADD, _ws)
 from .._lib import check, lib, ptr, stream_of
 
-_MEMO: "OrderedDict[tuple, tuple]" = OrderedDict()
-_MEMO_LOCK = threading.Lock()
+_MEMO: "OrderedDict[tuple, tuple]" = OrderedDict()      # key -> (out, out._version, weakref(input), N)
+_MEMO_LOCK = threading.RLock()
 _MEMO_MAX = 32
+_MEMO_MAX_BYTES = 8 << 30
+
+
+def clear_memo():
+    with _MEMO_LOCK:
+        _MEMO.clear()
 
 
 def _num_nodes(edge_index, num_nodes):
@@ -28,36 +35,63 @@ def _num_nodes(edge_index, num_nodes):
     return int(edge_index.max()) + 1 if edge_index.numel() else 0
 
 
-def _edit(edge_index: torch.Tensor, N: int, mode: int, filter_only: bool = False) -> torch.Tensor:
-    """Edited edge list as int64 [2, nnz] (memoised).  filter_only: drop loops, append none."""
-    _lib.require_cuda(edge_index, "edge_index")
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), N, mode, filter_only)
+def _memo_key(edge_index, N, mode, filter_only):
+    return (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
+            str(edge_index.device), N, mode, filter_only)
+
+
+def _memo_get(key, edge_index):
+    """The memoised result, unless the input tensor is not the one the entry was made from or somebody has
+    edited the handed-out result in place since (every caller receives the same tensor object)."""
     with _MEMO_LOCK:
         hit = _MEMO.get(key)
-        if hit is not None:
-            _MEMO.move_to_end(key)
-            return hit[0]
+        if hit is None:
+            return None
+        if hit[2]() is not edge_index or hit[0]._version != hit[1]:
+            del _MEMO[key]
+            return None
+        _MEMO.move_to_end(key)
+        return hit
+
+
+def _edit(edge_index: torch.Tensor, N, mode: int, filter_only: bool = False) -> torch.Tensor:
+    """Edited edge list as int64 [2, nnz] (memoised on the identity of the input tensor, which the entry does
+    not keep alive).  filter_only: drop loops, append none.  N=None: max id + 1, computed (one reduction + host
+    sync) only on a miss -- my_SAGEConv.forward calls remove_self_loops without a node count on every layer of
+    every forward (graphsage.py:55)."""
+    _lib.require_cuda(edge_index, "edge_index")
+    key = _memo_key(edge_index, N, mode, filter_only)
+    hit = _memo_get(key, edge_index)
+    if hit is not None:
+        return hit[0]
+    Nn = _num_nodes(edge_index, N)
     L = lib()
     dev = edge_index.device
     ei = edge_index.contiguous()
     E = ei.size(1)
-    e_src = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
-    e_dst = torch.empty(max(E + N, 1), dtype=torch.int32, device=dev)
+    e_src = torch.empty(max(E + Nn, 1), dtype=torch.int32, device=dev)
+    e_dst = torch.empty(max(E + Nn, 1), dtype=torch.int32, device=dev)
     nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
-    ws = _ws(L.rgbmp_edge_edit_workspace_bytes(E, N), dev)
-    check(L.rgbmp_edge_edit(ptr(ei[0]) if E else None, ptr(ei[1]) if E else None, E, N, mode, ptr(e_src), ptr(e_dst),
+    ws = _ws(L.rgbmp_edge_edit_workspace_bytes(E, Nn), dev)
+    check(L.rgbmp_edge_edit(ptr(ei[0]) if E else None, ptr(ei[1]) if E else None, E, Nn, mode, ptr(e_src), ptr(e_dst),
                             ptr(nnz_dev), ptr(ws), ws.numel(), dev.index, stream_of(dev)), "edge_edit")
     nnz = int(nnz_dev.item())
     if nnz < 0:
-        raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
+        raise RuntimeError(f"edge_index contains node ids outside [0, {Nn})")
     if filter_only:
-        nnz -= N
+        nnz -= Nn
     out = torch.stack([e_src[:nnz], e_dst[:nnz]]).to(torch.int64)
     with _MEMO_LOCK:
-        _MEMO[key] = (out, edge_index)
-        while len(_MEMO) > _MEMO_MAX:
+        _MEMO[key] = (out, out._version, weakref.ref(edge_index, lambda _r, k=key: _memo_drop(k)), Nn)
+        while len(_MEMO) > 1 and (len(_MEMO) > _MEMO_MAX or
+                                  sum(v[0].numel() * 8 for v in _MEMO.values()) > _MEMO_MAX_BYTES):
             _MEMO.popitem(last=False)
     return out
+
+
+def _memo_drop(key):
+    with _MEMO_LOCK:
+        _MEMO.pop(key, None)
 
 
 def remove_self_loops(edge_index, edge_attr=None):
@@ -65,15 +99,14 @@ def remove_self_loops(edge_index, edge_attr=None):
     if edge_attr is not None:
         mask = edge_index[0] != edge_index[1]
         return edge_index[:, mask], edge_attr[mask]
-    N = _num_nodes(edge_index, None)
-    return _edit(edge_index, N, LOOP_REMOVE_THEN_ADD, filter_only=True), None
+    return _edit(edge_index, None, LOOP_REMOVE_THEN_ADD, filter_only=True), None
 
 
 def add_self_loops(edge_index, edge_weight=None, fill_value=1.0, num_nodes=None):
     """A2 (graphsage.py:56)."""
-    N = _num_nodes(edge_index, num_nodes)
-    out = _edit(edge_index, N, LOOP_ADD)
+    out = _edit(edge_index, None if num_nodes is None else int(num_nodes), LOOP_ADD)
     if edge_weight is not None:
+        N = _num_nodes(edge_index, num_nodes)
         edge_weight = torch.cat([edge_weight, edge_weight.new_full((N,), fill_value)])
     return out, edge_weight
 

@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--feature-groups", type=int, default=0)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--as-called", action="store_true", help="1 GPU: also time the epoch through the reference's own classes")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     lr_ = int(os.environ.get("LOCAL_RANK", 0))
@@ -65,6 +66,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     res = run(args, rank, world, dev)
+    if args.as_called and world == 1:
+        res["as_called"] = run_as_called(args, dev)
     if rank == 0:
         print(json.dumps(res), flush=True)
     if world > 1:
@@ -73,9 +76,100 @@ def main():
 
 def default_args(**kw):
     """The argument set of main() as a namespace (bench.py calls run() with it)."""
-    d = dict(workload="products", hidden=64, K=10, alpha=0.1, epochs=5, warmup=2, feature_groups=0, check=False)
+    d = dict(workload="products", hidden=64, K=10, alpha=0.1, epochs=5, warmup=2, feature_groups=0, check=False,
+             as_called=False)
     d.update(kw)
     return argparse.Namespace(**d)
+
+
+def reference_root():
+    snap = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(snap, "rgb_experiment")):
+        return snap
+    return "/root/reference" if os.path.isdir("/root/reference/rgb_experiment") else None
+
+
+def run_as_called(args, dev, sg=None):
+    """The epoch AS THE REFERENCE CALLS IT (SURVEY.md 8d "metrics sync included"), single GPU: the reference's own
+    model class (models/appnp_stack.py:19-31, imported unmodified from baseline/_ref) over the product shim's
+    APPNP, and the reference's own `test()` / `compare_pred_label()` (itexperiments.py:600-664: three host syncs and
+    four sklearn metric calls per evaluation) driven by the statements of its epoch loop (:417-473, restated below
+    line by line because the loop lives inside the monolithic experiment()).  Wall clock per epoch, GPU drained
+    at the end of every epoch by the loop's own .item() calls."""
+    import copy
+    root = reference_root()
+    if root is None:
+        return {"unavailable": "no reference snapshot (baseline/_ref) on this box"}
+    import rgb_experiment_b200 as P
+    import rgb_experiment_b200.synth as S
+    P.install_shim()
+    sys.path.insert(0, root)
+    try:
+        import rgb_experiment.itexperiments as it
+        from rgb_experiment.models import APPNPStack as RefAPPNPStack
+    finally:
+        sys.path.remove(root)
+    if sg is None:
+        sg = S.make_named(args.workload, device=dev)
+    N, Fin, C = sg.num_nodes, sg.x.size(1), sg.num_classes
+    y, features, edge_index = sg.y, sg.x, sg.edge_index
+    sel = (S._mix(torch.arange(N, device=dev)) % 10)
+    train_mask, val_mask, test_mask = sel < 6, (sel >= 6) & (sel < 8), sel >= 8
+    torch.manual_seed(14530529)
+    model = RefAPPNPStack(input_dim=Fin, output_dim=C, hidden_unit=args.hidden, dropout_rate=0.5, alpha=args.alpha, K=args.K)
+    model.to(dev)
+    optimizer = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0)
+    criterion = nn.NLLLoss()
+    model_forward_param = {"x": features, "edge_index": edge_index}
+    metric_s = [0.0]
+    real_cmp = it.compare_pred_label
+
+    def timed_cmp(*a, **k):                     # same function, its host time (device sync + sklearn) accumulated
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = real_cmp(*a, **k)
+        metric_s[0] += time.perf_counter() - t0
+        return r
+
+    it.compare_pred_label = timed_cmp
+    state = {"best": 0.0, "best_model": None}
+
+    def epoch(i):
+        model.train()                                                               # :419
+        optimizer.zero_grad()
+        model_out = model(**model_forward_param)                                    # :427
+        out = model_out["out"]
+        loss = criterion(out[train_mask], y[train_mask])
+        it.compare_pred_label(out[train_mask].max(dim=1)[1], y[train_mask], True)   # :434
+        loss.item()                                                                 # :437
+        loss.backward()
+        optimizer.step()
+        val_dict = it.test(model, model_forward_param, y, val_mask, True)           # :464
+        criterion(val_dict["test_op"][val_mask], y[val_mask]).item()
+        test_dict = it.test(model, model_forward_param, y, test_mask, True)         # :470
+        criterion(test_dict["test_op"][test_mask], y[test_mask]).item()
+        if val_dict["ACC"] >= state["best"]:                                        # :491-494
+            state["best"] = val_dict["ACC"]
+            state["best_model"] = copy.deepcopy(model.state_dict())
+        return val_dict["ACC"], test_dict["ACC"]
+
+    try:
+        for i in range(args.warmup):
+            epoch(i)
+        torch.cuda.synchronize()
+        metric_s[0] = 0.0
+        t0 = time.perf_counter()
+        for i in range(args.epochs):
+            v, t = epoch(i)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / args.epochs * 1e3
+    finally:
+        it.compare_pred_label = real_cmp
+    m_ms = metric_s[0] / args.epochs * 1e3
+    return {"config": f"reference APPNPStack class + reference test()/compare_pred_label, {args.workload}-shaped, as called",
+            "epoch_wall_ms": round(wall, 2), "of_which_metrics_host_ms": round(m_ms, 2),
+            "epoch_wall_ms_without_metric_calls": round(wall - m_ms, 2),
+            "graph_builds": P.graph.stats["builds"], "val_acc": round(v, 4), "test_acc": round(t, 4)}
 
 
 def run(args, rank, world, dev):
@@ -98,7 +192,7 @@ def run(args, rank, world, dev):
 
     if world == 1:
         g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
-        prop = lambda h: P.ops.appnp(h, g, args.K, args.alpha, True)
+        prop = lambda h: P.ops.appnp(h, g, args.K, args.alpha)        # the shim's default form (ops.FOLD_KHOP)
         bn = nn.BatchNorm1d(args.hidden)
         lo, hi, R = 0, N, N
         grid = None
@@ -186,7 +280,7 @@ def run(args, rank, world, dev):
     if args.check:
         # first training step: logits + weight gradients vs the single-GPU model on every rank's own GPU
         g1 = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
-        m1 = APPNPStack(Fin, args.hidden, C, lambda h: P.ops.appnp(h, g1, args.K, args.alpha, True),
+        m1 = APPNPStack(Fin, args.hidden, C, lambda h: P.ops.appnp(h, g1, args.K, args.alpha),
                         nn.BatchNorm1d(args.hidden)).to(dev)
         m1.lin1.load_state_dict(ref_lin1.state_dict())
         m1.lin2.load_state_dict(ref_lin2.state_dict())
