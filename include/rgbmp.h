@@ -155,7 +155,7 @@ typedef struct rgbmp_graph {
   const int64_t* item_start;   /* [n_items]                                                         */
   const int32_t* row_order;    /* [n_rows] schedule of the short-row kernel, or NULL = natural order */
   int32_t        col_tagged;   /* 1: bit 31 of col[k] marks a frequently gathered ("hot") column, see
-                                  rgbmp_col_tag; only rgbmp_spmm / rgbmp_khop / rgbmp_gat_* accept it      */
+                                  rgbmp_col_tag; only rgbmp_spmm / rgbmp_khop accept it      */
 } rgbmp_graph_t;
 
 /* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
@@ -259,28 +259,47 @@ int rgbmp_peer_close(void* ptr, int device);
  * (c) attention kernels
  * ------------------------------------------------------------------------------------------ */
 
-/* Fused GATConv edge-softmax + weighted aggregate (gat.py:18-21,28-30).
- *   Xp [N,H*C] (ldx), a_src [n_cols,H], a_dst [n_rows,H]; per row i over in-edges j:
- *   e = leaky_relu(a_src[j]+a_dst[i]); alpha = exp(e-max)/(sum+1e-16); out[i] = sum alpha*Xp[j].
- * Saves rowmax,rowsum [n_rows,H] for the backward.  drop (optional, CSR order [nnz,H]) is the
- * attention-dropout keep-mask already divided by (1-p). */
-size_t rgbmp_gat_workspace_bytes(const rgbmp_graph_t* g, int H, int C);
-int rgbmp_gat_forward(const rgbmp_graph_t* g, const float* Xp, int64_t ldx,
-                      const float* a_src, const float* a_dst, int H, int C, float slope,
+/* Fused edge-score attention + weighted aggregate, one kernel family for the three layers of the reference whose
+ * per-edge weight is a function of the two endpoints (csrc/att.cu).  For target row i over its in-edges j -> i:
+ *   RGBMP_ATT_GAT  GATConv (gat.py:18-21,28-30):
+ *                  e = leaky_relu(a_nbr[j] + a_own[i]);  alpha = exp(e - max)/(sum + 1e-16);  out[i] = sum alpha*mask*X[j]
+ *   RGBMP_ATT_MX   SuperGATConv, MX attention (supergat.py:15-21; A12):
+ *                  e = leaky_relu((a_nbr[j] + a_own[i]) * sigmoid(<X[i,h,:], X[j,h,:]>)), then as GAT
+ *   RGBMP_ATT_FA   FAConv (fagcn.py:15,31; A13), H = 1:
+ *                  out[i] = sum tanh(a_nbr[j] + a_own[i]) * dinv[j]*dinv[i] * mask * X[j]        (no softmax)
+ * X [n_cols, H*C] (ldx), a_nbr [n_cols,H] (a_src / att_l side), a_own [n_rows,H] (a_dst / att_r side).
+ * Shapes: H == 1 with any C <= 128 (padding columns of X up to roundup(C,4) must be ZERO), or C a power of two in
+ * 8..128 with any H (heads are tiled over the grid) -- rgbmp_att_supported() says which; the host layer pads heads.
+ * drop (optional, forward-CSR order [nnz,H]) is the attention-dropout keep-mask already divided by (1-p).
+ * Softmax scores save rowmax,rowsum [n_rows,H].  TRAINING mode = out2 != NULL: GAT and FA accumulate a second
+ * aggregate next to out (GAT: P_i = sum alpha*leaky'*mask*X[j] into out2 and q_i = sum alpha*leaky' into rowq;
+ * FA: Q_i = sum (1-tanh^2)*dinv*dinv*mask*X[j]) from which the backward gets the gradient of the per-TARGET score
+ * term without atomics (da_own[i] = <dout_i, P_i> - S_i q_i); MX needs none (out2 must be NULL).
+ * Nothing edge-sized is written; the result is deterministic. */
+#define RGBMP_ATT_GAT 0
+#define RGBMP_ATT_MX  1
+#define RGBMP_ATT_FA  2
+int rgbmp_att_supported(int score, int H, int C);
+size_t rgbmp_att_forward_workspace_bytes(const rgbmp_graph_t* g, int H, int C);
+int rgbmp_att_forward(const rgbmp_graph_t* g, int score, const float* X, int64_t ldx,
+                      const float* a_nbr, const float* a_own, const float* dinv, int H, int C, float slope,
                       const float* drop, float* out, int64_t ldo, float* rowmax, float* rowsum,
+                      float* out2, int64_t ldo2, float* rowq,
                       void* ws, size_t ws_bytes, int device, void* stream);
 
-/* Backward on the TRANSPOSE CSR gT (rows = sources j).  `out` is the forward result (the softmax
- * backward needs S[i,h] = <dout[i,h,:], out[i,h,:]>, computed inside).  Writes dXp [n_src,H*C],
- * da_src [n_src,H]; accumulates da_dst [n_dst,H] (must be zero on entry).  eid_map_T: for drop (CSR order) lookup, tpos[k'] gives the
- * forward-CSR position of transpose entry k' (NULL when drop is NULL). */
-size_t rgbmp_gat_backward_workspace_bytes(const rgbmp_graph_t* gT, int64_t n_dst, int H, int C);
-int rgbmp_gat_backward(const rgbmp_graph_t* gT, const float* Xp, int64_t ldx,
-                       const float* a_src, const float* a_dst, int H, int C, float slope,
+/* Backward of rgbmp_att_forward.  g = the forward CSR, gT = its transpose (rows = sources j).  Recomputes the
+ * edge weights from the saved per-target statistics; `out`/`out2`/`rowq` are the training-mode forward's results.
+ * Writes dX [n, H*C] (lddx), da_nbr [n_cols,H], da_own [n_rows,H].  MX runs one pass per orientation (the logit
+ * <x_i,x_j> feeds both endpoints) and needs the scratch dXf [n_rows, lddxf]; GAT and FA run one transpose pass.
+ * tpos[k'] = forward-CSR position of transpose entry k' (only read when drop != NULL). */
+size_t rgbmp_att_backward_workspace_bytes(const rgbmp_graph_t* g, const rgbmp_graph_t* gT, int H, int C);
+int rgbmp_att_backward(const rgbmp_graph_t* g, const rgbmp_graph_t* gT, int score, const float* X, int64_t ldx,
+                       const float* a_nbr, const float* a_own, const float* dinv, int H, int C, float slope,
                        const float* drop, const int32_t* tpos,
-                       const float* rowmax, const float* rowsum, const float* out, int64_t ldo,
+                       const float* rowmax, const float* rowsum, const float* rowq,
+                       const float* out, int64_t ldo, const float* out2, int64_t ldo2,
                        const float* dout, int64_t ldd,
-                       float* dXp, int64_t lddx, float* da_src, float* da_dst, int64_t n_dst,
+                       float* dX, int64_t lddx, float* dXf, int64_t lddxf, float* da_nbr, float* da_own,
                        void* ws, size_t ws_bytes, int device, void* stream);
 
 /* S[i,h] = sum_c A[i,h*C+c]*B[i,h*C+c] */

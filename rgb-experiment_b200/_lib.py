@@ -72,13 +72,14 @@ def lib():
                                        c_vp, c_sz, C.c_int, c_vp]),
     }
     optional = {
-        "rgbmp_gat_workspace_bytes": (c_sz, [GP, C.c_int, C.c_int]),
-        "rgbmp_gat_forward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_i64, c_vp,
-                                        c_vp, c_vp, c_sz, C.c_int, c_vp]),
-        "rgbmp_gat_backward_workspace_bytes": (c_sz, [GP, c_i64, C.c_int, C.c_int]),
-        "rgbmp_gat_backward": (C.c_int, [GP, c_vp, c_i64, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp, c_vp,
-                                         c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz,
-                                         C.c_int, c_vp]),
+        "rgbmp_att_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+        "rgbmp_att_forward_workspace_bytes": (c_sz, [GP, C.c_int, C.c_int]),
+        "rgbmp_att_forward": (C.c_int, [GP, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_i64,
+                                        c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, C.c_int, c_vp]),
+        "rgbmp_att_backward_workspace_bytes": (c_sz, [GP, GP, C.c_int, C.c_int]),
+        "rgbmp_att_backward": (C.c_int, [GP, GP, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                         c_vp, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_coalesce_workspace_bytes": (c_sz, [c_i64, c_i64, C.c_int]),
         "rgbmp_coalesce": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_peer_alloc": (C.c_int, [c_sz, c_vp, c_vp, C.c_int]),

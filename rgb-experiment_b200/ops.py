@@ -466,70 +466,146 @@ def spmm_heads(w, X, graph, H, Cc):
     return _SpmmHeads.apply(w, X, graph, H, Cc)
 
 
-def gat_fusable(H: int, Cc: int) -> bool:
-    if H * Cc > 128:
-        return False
+ATT_GAT, ATT_MX, ATT_FA = 0, 1, 2
+
+
+def _head_pad(H: int, Cc: int) -> int:
+    """Channels per head the fused kernels run with: C itself for a single head, else the next power of two >= 8
+    (a lane's 8 channels must stay inside one head; zero channels change neither dot products nor sums)."""
     if H == 1:
-        return True
-    q = Cc // 4
-    return Cc % 4 == 0 and q > 0 and (q & (q - 1)) == 0
+        return Cc
+    c = 8
+    while c < Cc:
+        c <<= 1
+    return c
 
 
-class _GAT(torch.autograd.Function):
-    """Fused GATConv attention + aggregate (A10/A11; gat.py:18-21).  Saves only the per-node
-    softmax statistics (max, sum) [N,H]; alpha is recomputed in the backward."""
+def att_fusable(score: int, H: int, Cc: int) -> bool:
+    return bool(lib().rgbmp_att_supported(score, H, _head_pad(H, Cc)))
+
+
+def gat_fusable(H: int, Cc: int) -> bool:
+    return att_fusable(ATT_GAT, H, Cc)
+
+
+def _rows_zero_padded(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """as_rows, but the padding columns up to roundup(F,4) are guaranteed ZERO (the H == 1 kernels take dot
+    products over whole float4 vectors)."""
+    F = x.size(1)
+    if F % 4 == 0:
+        return as_rows(x)
+    Fp = padded_width(F, x.dtype)
+    buf = torch.zeros((x.size(0), Fp), dtype=x.dtype, device=x.device)
+    buf[:, :F].copy_(x)
+    return buf[:, :F], Fp
+
+
+class _Att(torch.autograd.Function):
+    """Fused edge-score attention + aggregate (csrc/att.cu): GATConv (A10/A11; gat.py:18-21), SuperGATConv-MX
+    (A12; supergat.py:15-21) and FAConv (A13; fagcn.py:15,31).  Nothing edge-sized is allocated: the forward saves
+    per-node statistics (max, sum and -- in training mode -- the second aggregate that yields the gradient of the
+    target-side score term), the backward recomputes the edge weights.  Deterministic (no atomics)."""
 
     @staticmethod
-    def forward(ctx, xp, a_src, a_dst, graph: Graph, H: int, Cc: int, slope: float, drop_csr):
-        xb, ldx = as_rows(xp)
-        a_s, a_d = a_src.contiguous(), a_dst.contiguous()
-        N = graph.N
-        out, ldo = alloc_rows(N, H * Cc, torch.float32, xp.device)
-        rmax = torch.empty((N, H), dtype=torch.float32, device=xp.device)
-        rsum = torch.empty((N, H), dtype=torch.float32, device=xp.device)
-        dev = xp.device
-        wsb = lib().rgbmp_gat_workspace_bytes(graph.fwd.ref, H, Cc)
+    def forward(ctx, x, a_nbr, a_own, graph: Graph, score: int, H: int, Cc: int, slope: float, drop_csr):
+        _lib.require_cuda(x, "x")
+        xb, ldx = _rows_zero_padded(x)
+        a_n, a_o = a_nbr.contiguous().view(-1, H), a_own.contiguous().view(-1, H)
+        N, dev = graph.N, x.device
+        train = any(ctx.needs_input_grad[:3])
+        out, ldo = alloc_rows(N, H * Cc, torch.float32, dev)
+        rmax = rsum = rowq = out2 = dinv = None
+        ldo2 = 0
+        if score != ATT_FA:
+            rmax = torch.empty((N, H), dtype=torch.float32, device=dev)
+            rsum = torch.empty((N, H), dtype=torch.float32, device=dev)
+        else:
+            dinv = graph.dinv()
+        if train and score != ATT_MX:
+            out2, ldo2 = alloc_rows(N, H * Cc, torch.float32, dev)
+            if score == ATT_GAT:
+                rowq = torch.empty((N, H), dtype=torch.float32, device=dev)
+        L = lib()
+        wsb = L.rgbmp_att_forward_workspace_bytes(graph.fwd.ref, H, Cc)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        check(lib().rgbmp_gat_forward(graph.fwd.ref, ptr(xb), ldx, ptr(a_s), ptr(a_d), H, Cc, slope, ptr(drop_csr),
-                                      ptr(out), ldo, ptr(rmax), ptr(rsum), ptr(ws), wsb, dev.index, stream_of(dev)),
-              "gat_forward")
-        ctx.graph, ctx.H, ctx.Cc, ctx.slope = graph, H, Cc, slope
-        ctx.save_for_backward(xb, a_s, a_d, rmax, rsum, out, drop_csr)
+        check(L.rgbmp_att_forward(graph.fwd.ref, score, ptr(xb), ldx, ptr(a_n), ptr(a_o), ptr(dinv), H, Cc, slope,
+                                  ptr(drop_csr), ptr(out), ldo, ptr(rmax), ptr(rsum), ptr(out2), ldo2, ptr(rowq),
+                                  ptr(ws), wsb, dev.index, stream_of(dev)), "att_forward")
+        ctx.graph, ctx.score, ctx.H, ctx.Cc, ctx.slope = graph, score, H, Cc, slope
+        ctx.save_for_backward(xb, a_n, a_o, rmax, rsum, rowq, out, out2, drop_csr)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xb, a_s, a_d, rmax, rsum, out, drop = ctx.saved_tensors
-        g, H, Cc = ctx.graph, ctx.H, ctx.Cc
-        dev = dout.device
-        db, ldd = as_rows(dout)
-        N = g.N
-        dxp, lddx = alloc_rows(N, H * Cc, torch.float32, dev)
-        da_s = torch.empty((N, H), dtype=torch.float32, device=dev)
-        da_d = torch.zeros((N, H), dtype=torch.float32, device=dev)
+        xb, a_n, a_o, rmax, rsum, rowq, out, out2, drop = ctx.saved_tensors
+        g, score, H, Cc = ctx.graph, ctx.score, ctx.H, ctx.Cc
+        dev, N = dout.device, g.N
+        db, ldd = _rows_zero_padded(dout)
+        dx, lddx = alloc_rows(N, H * Cc, torch.float32, dev)
+        dxf, lddxf = (alloc_rows(N, H * Cc, torch.float32, dev) if score == ATT_MX else (None, 0))
+        da_n = torch.empty((N, H), dtype=torch.float32, device=dev)
+        da_o = torch.empty((N, H), dtype=torch.float32, device=dev)
         tpos = g.tpos() if drop is not None else None
-        wsb = lib().rgbmp_gat_backward_workspace_bytes(g.bwd.ref, N, H, Cc)
+        dinv = g.dinv() if score == ATT_FA else None
+        L = lib()
+        wsb = L.rgbmp_att_backward_workspace_bytes(g.fwd.ref, g.bwd.ref, H, Cc)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        check(lib().rgbmp_gat_backward(g.bwd.ref, ptr(xb), xb.stride(0), ptr(a_s), ptr(a_d), H, Cc, ctx.slope,
-                                       ptr(drop), ptr(tpos), ptr(rmax), ptr(rsum), ptr(out), out.stride(0), ptr(db), ldd,
-                                       ptr(dxp), lddx, ptr(da_s), ptr(da_d), N, ptr(ws), wsb, dev.index,
-                                       stream_of(dev)), "gat_backward")
-        return dxp, da_s, da_d, None, None, None, None, None
+        check(L.rgbmp_att_backward(g.fwd.ref, g.bwd.ref, score, ptr(xb), xb.stride(0), ptr(a_n), ptr(a_o), ptr(dinv), H, Cc,
+                                   ctx.slope, ptr(drop), ptr(tpos), ptr(rmax), ptr(rsum), ptr(rowq), ptr(out),
+                                   out.stride(0), ptr(out2), 0 if out2 is None else out2.stride(0), ptr(db), ldd,
+                                   ptr(dx), lddx, ptr(dxf), lddxf, ptr(da_n), ptr(da_o), ptr(ws), wsb, dev.index,
+                                   stream_of(dev)), "att_backward")
+        return dx, da_n, da_o, None, None, None, None, None, None
+
+
+def _att(score: int, name: str, x, a_nbr, a_own, graph: Graph, H: int, Cc: int, slope: float, drop_edge):
+    """Pads heads to the kernel's channel count (torch ops on node-sized tensors, autograd-transparent), memoises
+    the no-grad call, applies the fused op."""
+    Cp = _head_pad(H, Cc)
+    N = x.size(0)
+    xk = x if Cp == Cc else torch.nn.functional.pad(x.view(N, H, Cc), (0, Cp - Cc)).reshape(N, H * Cp)
+    drop_csr = None if drop_edge is None else graph.to_csr_order(drop_edge)
+    if drop_csr is None:
+        out = memo.cached(graph, (name, H, Cc, float(slope)), (xk, a_nbr, a_own), _work(graph, xk),
+                          lambda: _Att.apply(xk, a_nbr, a_own, graph, score, H, Cp, float(slope), None))
+    else:
+        out = _Att.apply(xk, a_nbr, a_own, graph, score, H, Cp, float(slope), drop_csr)
+    return out if Cp == Cc else out.view(N, H, Cp)[:, :, :Cc].reshape(N, H * Cc)
 
 
 def gat(xp, a_src, a_dst, graph: Graph, H: int, Cc: int, slope: float = 0.2, drop_edge: Optional[torch.Tensor] = None):
     """xp [N,H*C], a_src/a_dst [N,H] -> [N,H*C].  drop_edge: optional [nnz,H] keep-mask/(1-p) in EDGE order."""
-    if gat_fusable(H, Cc):
-        if drop_edge is None:
-            return memo.cached(graph, ("gat", H, Cc, float(slope)), (xp, a_src, a_dst), _work(graph, xp),
-                               lambda: _GAT.apply(xp, a_src, a_dst, graph, H, Cc, float(slope), None))
-        drop_csr = graph.to_csr_order(drop_edge)
-        return _GAT.apply(xp, a_src, a_dst, graph, H, Cc, float(slope), drop_csr)
+    if att_fusable(ATT_GAT, H, Cc):
+        return _att(ATT_GAT, "gat", xp, a_src, a_dst, graph, H, Cc, slope, drop_edge)
     e = torch.nn.functional.leaky_relu(edge_u_add_v(a_src, a_dst, graph), slope)
     alpha = edge_softmax(e, graph)
     if drop_edge is not None:
         alpha = alpha * graph.to_csr_order(drop_edge)
     return spmm_heads(alpha, xp, graph, H, Cc)
+
+
+def supergat_mx(xp, a_l, a_r, graph: Graph, H: int, Cc: int, slope: float = 0.2,
+                drop_edge: Optional[torch.Tensor] = None):
+    """SuperGATConv MX attention + aggregate (A12): alpha = softmax(leaky_relu((a_l[j] + a_r[i]) * sigmoid(<x_i, x_j>)))."""
+    if att_fusable(ATT_MX, H, Cc):
+        return _att(ATT_MX, "supergat_mx", xp, a_l, a_r, graph, H, Cc, slope, drop_edge)
+    logits = edge_sddmm(xp, xp, graph, H, Cc)
+    alpha = torch.nn.functional.leaky_relu(edge_u_add_v(a_l, a_r, graph) * logits.sigmoid(), slope)
+    alpha = edge_softmax(alpha, graph)
+    if drop_edge is not None:
+        alpha = alpha * graph.to_csr_order(drop_edge)
+    return spmm_heads(alpha, xp, graph, H, Cc)
+
+
+def faconv(x, a_l, a_r, graph: Graph, drop_edge: Optional[torch.Tensor] = None):
+    """FAConv aggregate (A13): out[i] = sum_j tanh(a_l[j] + a_r[i]) * gcn_norm_ij * mask_ij * x[j]; a_l, a_r [N,1]."""
+    Cc = x.size(1)
+    if att_fusable(ATT_FA, 1, Cc):
+        return _att(ATT_FA, "faconv", x, a_l, a_r, graph, 1, Cc, 0.0, None if drop_edge is None else drop_edge.view(-1, 1))
+    c = edge_u_add_v(a_l.view(-1, 1), a_r.view(-1, 1), graph).tanh()
+    if drop_edge is not None:
+        c = c * graph.to_csr_order(drop_edge).view(-1, 1)
+    return spmm_heads(c * graph.gcn_val(False).view(-1, 1), x, graph, 1, Cc)
 
 
 class _EidView:

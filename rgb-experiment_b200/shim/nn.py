@@ -221,8 +221,9 @@ class GATConv(MessagePassing):
 
 
 class SuperGATConv(MessagePassing):
-    """A12, MX attention (models/supergat.py:15-21,26,29).  Scores: SDDMM + u_add_v kernels,
-    edge softmax + weighted multi-head SpMM kernels; edge sampling and the BCE loss stay PyTorch."""
+    """A12, MX attention (models/supergat.py:15-21,26,29): scores, edge softmax and aggregate in ONE fused
+    kernel pass (ops.supergat_mx, csrc/att.cu; backward = one pass per orientation, nothing edge-sized is
+    allocated).  Edge sampling and the BCE loss on the sampled pairs stay PyTorch (node-pair sized)."""
 
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
                  add_self_loops=True, bias=True, attention_type="MX", neg_sample_ratio=0.5,
@@ -276,19 +277,19 @@ class SuperGATConv(MessagePassing):
         g = get_graph(edge_index, N, LOOP_REMOVE_THEN_ADD if self.add_self_loops else LOOP_NONE)
         xp = self.lin(x)
         x3 = xp.view(-1, H, C)
-        logits = ops.edge_sddmm(xp, xp, g, H, C)                       # <x_i, x_j> per head, CSR order
+        keep = None
+        if self.training and self.dropout > 0:                        # PyTorch RNG mask, edge order (like GATConv)
+            keep = F.dropout(torch.ones((g.nnz, H), device=x.device), p=self.dropout, training=True)
         if self.attention_type == "MX":
             a_l = (x3 * self.att_l).sum(-1)
             a_r = (x3 * self.att_r).sum(-1)
-            alpha = ops.edge_u_add_v(a_l, a_r, g) * logits.sigmoid()
-        else:
-            alpha = logits / math.sqrt(C)
-        alpha = F.leaky_relu(alpha, self.negative_slope)
-        alpha = ops.edge_softmax(alpha, g)
-        if self.training and self.dropout > 0:
-            keep = F.dropout(torch.ones((g.nnz, H), device=x.device), p=self.dropout, training=True)
-            alpha = alpha * g.to_csr_order(keep)
-        out = ops.spmm_heads(alpha, xp, g, H, C)
+            out = ops.supergat_mx(xp, a_l, a_r, g, H, C, self.negative_slope, keep)      # one fused pass
+        else:                                                         # SD attention: not used by the reference
+            alpha = F.leaky_relu(ops.edge_sddmm(xp, xp, g, H, C) / math.sqrt(C), self.negative_slope)
+            alpha = ops.edge_softmax(alpha, g)
+            if keep is not None:
+                alpha = alpha * g.to_csr_order(keep)
+            out = ops.spmm_heads(alpha, xp, g, H, C)
         if self.training:
             ei = g.edge_index()
             pos_ei, _ = U.dropout_adj(ei, p=1.0 - self.edge_sample_ratio, training=True)
@@ -363,7 +364,7 @@ class SGConv(MessagePassing):
 
 
 class FAConv(MessagePassing):
-    """A13 (models/fagcn.py:15,31): c = tanh(a_l[j]+a_r[i]) * gcn weight -> weighted SpMM."""
+    """A13 (models/fagcn.py:15,31): out[i] = sum_j tanh(a_l[j]+a_r[i]) * gcn_norm_ij * x[j], fused (ops.faconv)."""
 
     def __init__(self, channels, eps=0.1, dropout=0.0, cached=False, add_self_loops=True, normalize=True, **kwargs):
         kwargs.setdefault("aggr", "add")
@@ -378,12 +379,10 @@ class FAConv(MessagePassing):
             raise NotImplementedError("FAConv(normalize=False) is not used by the reference")
         N = x.size(0)
         g = get_graph(edge_index, N, LOOP_ADD_REMAINING if self.add_self_loops else LOOP_NONE)
-        c = ops.edge_u_add_v(self.att_l(x), self.att_r(x), g).tanh()          # [nnz,1], CSR order
+        keep = None
         if self.training and self.dropout > 0:
             keep = F.dropout(torch.ones(g.nnz, device=x.device), p=self.dropout, training=True)
-            c = c * g.to_csr_order(keep).view(-1, 1)
-        w = c * g.gcn_val(False).view(-1, 1)
-        out = ops.spmm_heads(w, x, g, 1, x.size(1))
+        out = ops.faconv(x, self.att_l(x), self.att_r(x), g, keep)            # tanh score * gcn weight, fused
         if self.eps != 0.0:
             out = out + self.eps * x_0
         return out

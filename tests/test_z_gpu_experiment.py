@@ -60,9 +60,12 @@ def test_experiment_accuracy_matches_the_oracle_run(ref, name):
     finally:
         if restore is not None:
             restore()
-    acc_o = GOLD[name]["ACC"]
-    assert abs(r["ACC"] - acc_o) <= 0.005, (name, r["ACC"], acc_o)          # 0.5 pt
-    assert abs(float(r["f1_macro"]) - GOLD[name]["f1_macro"]) <= 0.01
+    # "the oracle's accuracy" = the interval its own runs span when only the host thread count (the fp32 summation
+    # order) changes -- a single point for the well-conditioned models, a full point wide for GIN (make_experiment_golden.py)
+    accs = list(GOLD[name].get("ACC_by_threads", {}).values()) + [GOLD[name]["ACC"]]
+    f1s = list(GOLD[name].get("f1_by_threads", {}).values()) + [GOLD[name]["f1_macro"]]
+    assert min(accs) - 0.005 <= r["ACC"] <= max(accs) + 0.005, (name, r["ACC"], accs)          # 0.5 pt
+    assert min(f1s) - 0.01 <= float(r["f1_macro"]) <= max(f1s) + 0.01
     if EC.CASES[name][1] not in ("mlp",):
         # the CSR is built once per (edge list, loop mode), not once per forward: a handful of builds for ~120 forwards
         assert R.graph.stats["builds"] - builds0 <= 6, R.graph.stats
