@@ -109,12 +109,23 @@ int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int
                        int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long, int64_t* item_start,
                        void* ws, size_t ws_bytes, int device, void* stream);
 
+/* The same lists with the long rows taken in the order of a row schedule (order[p] = row at position p, or NULL
+ * = natural order): the work items of one locality group are then adjacent in the long-row launch. */
+int rgbmp_longrow_fill_ordered(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk,
+                               const int32_t* order, int64_t n_long, int64_t n_items,
+                               int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long, int64_t* item_start,
+                               void* ws, size_t ws_bytes, int device, void* stream);
+
 /* Row schedule for the short-row SpMM kernel: rows sorted by degree (longest first) inside windows
  * of `window` consecutive rows, so that the rows sharing a warp have equal length (no divergence)
  * while coarse locality of neighbouring rows is kept.  order int32 [n_rows]. */
 size_t rgbmp_row_order_workspace_bytes(int64_t n_rows);
 int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order,
                     void* ws, size_t ws_bytes, int device, void* stream);
+/* ... sorted by (group[row], -degree) instead: group int32 [n_rows] with values in [0, n_groups), n_groups <= 32768
+ * (the locality groups of rgbmp_cluster_lpa, ranked by the host).  group == NULL: as rgbmp_row_order. */
+int rgbmp_row_order_grouped(const int64_t* rowptr, int64_t n_rows, int64_t window, const int32_t* group,
+                            int32_t n_groups, int32_t* order, void* ws, size_t ws_bytes, int device, void* stream);
 
 /* Sort an edge list by (row, col) and drop duplicate pairs = torch_sparse.coalesce(index, None, m, n)
  * (rd2pd.py:93); with symmetrize = 1 the list is first extended by every reversed edge =
@@ -242,6 +253,19 @@ int rgbmp_l2_persist(int device, size_t bytes, size_t* granted);
  * divide=1  Y[i,:] = X[i,:] / scale[i]  (backward of scatter-mean: grad / count). */
 int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, void* Y, int64_t ldy,
                     int64_t n_rows, int F, int dtype, int device, void* stream);
+
+/* Locality groups for the row schedule (csrc/cluster.cu; no reference counterpart -- PyG's scatter has no schedule).
+ * Seeded, leaves-first label propagation over the CSR g (square): the n_seeds (<= 4096) highest-degree nodes --
+ * the first entries of deg_order, a global rgbmp_row_order -- keep their own label; in round t < iters an
+ * unlabelled node takes the most frequent label among its labelled in-neighbours (ties: smallest label) once at
+ * least taus[t] (host array) of its neighbours carry one, and keeps it.  label int32 [n_rows] out, every value in
+ * [0, n_seeds).  Integer work, deterministic.  rgbmp_cluster_connectivity: W[a*n_groups + b] = number of CSR
+ * entries of rows labelled a whose column is labelled b (uint32 [n_groups^2], zeroed inside). */
+size_t rgbmp_cluster_workspace_bytes(int64_t n_rows);
+int rgbmp_cluster_lpa(const rgbmp_graph_t* g, const int32_t* deg_order, int32_t n_seeds, int iters,
+                      const float* taus, int32_t* label, void* ws, size_t ws_bytes, int device, void* stream);
+int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, uint32_t* W,
+                               int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (b2) peer memory for the row-partitioned multi-GPU path (one process per GPU, NVLink P2P)

@@ -60,6 +60,12 @@ def lib():
         "rgbmp_longrow_fill_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_longrow_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
                                          C.c_int, c_vp]),
+        "rgbmp_longrow_fill_ordered": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz,
+                                                 C.c_int, c_vp]),
+        "rgbmp_row_order_grouped": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_sz, C.c_int, c_vp]),
+        "rgbmp_cluster_workspace_bytes": (c_sz, [c_i64]),
+        "rgbmp_cluster_lpa": (C.c_int, [GP, c_vp, c_i32, C.c_int, C.POINTER(c_f32), c_vp, c_vp, c_sz, C.c_int, c_vp]),
+        "rgbmp_cluster_connectivity": (C.c_int, [GP, c_vp, c_i32, c_vp, C.c_int, c_vp]),
         "rgbmp_row_order_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_row_order": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_spmm_workspace_bytes": (c_sz, [GP, C.c_int]),

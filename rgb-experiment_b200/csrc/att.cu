@@ -27,6 +27,7 @@
 //   FA:   da_r[i] = <dout_i, Q_i>,  Q_i = sum_j (1 - tanh^2) dinv_j dinv_i mask_ij x_j, likewise;
 //   MX:   the logit <x_i, x_j> sends gradient to BOTH endpoints' features, so its backward runs one pass per
 //         orientation anyway (forward CSR: dX_i += dlogit x_j, da_r; transpose CSR: dX_j += alpha dout_i + dlogit x_i, da_l).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rgbmp {
@@ -185,13 +186,27 @@ struct FwdState {
   float4 acc[2], acc2[2];
 };
 
-template <int SC, bool TRAIN>
-__device__ __forceinline__ void fwd_consume(const AttParams& p, const float4 (&x)[U][2], const float (&sn)[U], const float (&dn)[U],
+// Column ids of a batch reach the lanes of a group through shared memory (one STS per lane, then broadcast LDS of
+// the UU ids of a step) instead of one SHFL per edge: a SHFL occupies the LSU data pipe for 4 wavefronts, the
+// same pipe that serves the gathers (profiles/r02_spmm_l1_wavefronts.txt).
+template <int N>
+__device__ __forceinline__ void lds_ids(const int32_t* p, uint32_t (&c)[N]) {
+  if constexpr (N == 4) {
+    const int4 v = *reinterpret_cast<const int4*>(p);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+  } else {
+    const int2 v = *reinterpret_cast<const int2*>(p);
+    c[0] = v.x; c[1] = v.y;
+  }
+}
+
+template <int SC, bool TRAIN, int UU>
+__device__ __forceinline__ void fwd_consume(const AttParams& p, const float4 (&x)[UU][2], const float (&sn)[UU], const float (&dn)[UU],
                                             int nvalid, int64_t kbase, const Lane& L, float so, float d_own,
                                             const float4 (&xi)[2], FwdState& st) {
   if constexpr (SC == SC_FA) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < UU; ++u) {
       if (u < nvalid) {
         const float t = tanhf(sn[u] + so);
         float wgt = dn[u] * d_own;
@@ -207,10 +222,10 @@ __device__ __forceinline__ void fwd_consume(const AttParams& p, const float4 (&x
       }
     }
   } else {
-    float e[U];
+    float e[UU];
     float mb = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < UU; ++u) {
       float raw = sn[u] + so;                               // log2 domain (both terms pre-scaled)
       if constexpr (SC == SC_MX) {
         const float dot = head_sum(dot4(xi[0], x[u][0]) + dot4(xi[1], x[u][1]), p.LPH);
@@ -232,7 +247,7 @@ __device__ __forceinline__ void fwd_consume(const AttParams& p, const float4 (&x
       st.m = mb;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < UU; ++u) {
       if (u < nvalid) {
         const float pe = ex2(e[u] - st.m);
         st.s += pe;
@@ -252,68 +267,94 @@ __device__ __forceinline__ void fwd_consume(const AttParams& p, const float4 (&x
   }
 }
 
-template <int SC, bool TRAIN, int G>
+// UU edges per step; PIPE: software-pipelined full batches (the gathers of step j+UU fly while step j is consumed)
+template <int SC, bool TRAIN, int G, int UU, bool PIPE>
 __device__ __forceinline__ void fwd_range(const AttParams& p, int64_t k0, int64_t k1, int gl, const Lane& L, float so,
-                                          float d_own, const float4 (&xi)[2], FwdState& st) {
+                                          float d_own, const float4 (&xi)[2], int32_t* sm_ids, FwdState& st) {
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
   const int maxlen = __reduce_max_sync(FULLMASK, len);
   if (maxlen == 0) return;
   const int32_t* __restrict__ col = p.col + k0;
   const char* xb0 = reinterpret_cast<const char*>(p.Xn + L.f);
-  const char* xb1 = reinterpret_cast<const char*>(p.Xn + L.f + (L.nact > 1 ? 4 : 0));
+  const char* xb1 = reinterpret_cast<const char*>(p.Xn + L.f + 4);
+  const bool a0 = L.nact > 0, a1 = L.nact > 1;             // lanes beyond the row issue no feature load
   const uint32_t row_bytes = (uint32_t)(p.ldn * 4);
   const char* snb = reinterpret_cast<const char*>(p.sn + L.h);
   const uint32_t sn_bytes = (uint32_t)(p.H * 4);
   auto gather = [&](uint32_t c, float4 (&xx)[2], float& aa, float& dd) {
-    xx[0] = __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)c * row_bytes));
-    xx[1] = __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)c * row_bytes));
+    xx[0] = a0 ? __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)c * row_bytes)) : zero4();
+    xx[1] = a1 ? __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)c * row_bytes)) : zero4();
     aa = __ldg(reinterpret_cast<const float*>(snb + (size_t)c * sn_bytes));
     if constexpr (SC == SC_FA) dd = __ldg(p.dinv + c);
     else dd = 0.f;
   };
-  int32_t cl = (gl < len) ? __ldcs(col + gl) : 0;
+  const int lane = threadIdx.x & 31;
+  int32_t* wids = sm_ids + (threadIdx.x & ~31);            // this warp's 32 slots
+  const int32_t* gids = wids + (lane - gl);                // this group's G slots
+  int32_t cn = (gl < len) ? __ldcs(col + gl) : 0;          // lanes past the row hold id 0: a valid row
   for (int off = 0; off < maxlen; off += G) {
     int nb = len - off;
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
-    int32_t cn = 0;
+    __syncwarp();
+    wids[lane] = cn;
+    __syncwarp();
+    cn = 0;
     if (off + G + gl < len) cn = __ldcs(col + off + G + gl);
-    if (G >= 2 * U && __all_sync(FULLMASK, nb == G)) {
-      // full batch in every group: software-pipelined -- the gathers of step j+U fly while step j is consumed
-      float4 x[U][2];
-      float as[U], dn[U];
+    if (G >= 2 * UU && __all_sync(FULLMASK, nb == G)) {
+      if constexpr (PIPE) {
+        float4 x[UU][2];
+        float as[UU], dn[UU];
+        {
+          uint32_t c[UU];
+          lds_ids<UU>(gids, c);
 #pragma unroll
-      for (int u = 0; u < U; ++u) gather((uint32_t)__shfl_sync(FULLMASK, cl, u, G), x[u], as[u], dn[u]);
+          for (int u = 0; u < UU; ++u) gather(c[u], x[u], as[u], dn[u]);
+        }
 #pragma unroll 1
-      for (int j = 0; j < G; j += U) {
-        float4 xn[U][2];
-        float asn[U], dnn[U];
-        const int jn = (j + U < G) ? j + U : j;            // last step re-requests itself (L1 hit, unused)
+        for (int j = 0; j < G; j += UU) {
+          float4 xn[UU][2];
+          float asn[UU], dnn[UU];
+          const int jn = (j + UU < G) ? j + UU : j;          // last step re-requests itself (L1 hit, unused)
+          uint32_t c[UU];
+          lds_ids<UU>(gids + jn, c);
 #pragma unroll
-        for (int u = 0; u < U; ++u) gather((uint32_t)__shfl_sync(FULLMASK, cl, jn + u, G), xn[u], asn[u], dnn[u]);
-        fwd_consume<SC, TRAIN>(p, x, as, dn, U, k0 + off + j, L, so, d_own, xi, st);
+          for (int u = 0; u < UU; ++u) gather(c[u], xn[u], asn[u], dnn[u]);
+          fwd_consume<SC, TRAIN, UU>(p, x, as, dn, UU, k0 + off + j, L, so, d_own, xi, st);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          as[u] = asn[u];
-          dn[u] = dnn[u];
-          x[u][0] = xn[u][0];
-          x[u][1] = xn[u][1];
+          for (int u = 0; u < UU; ++u) {
+            as[u] = asn[u];
+            dn[u] = dnn[u];
+            x[u][0] = xn[u][0];
+            x[u][1] = xn[u][1];
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < G; j += UU) {
+          float4 x[UU][2];
+          float as[UU], dn[UU];
+          uint32_t c[UU];
+          lds_ids<UU>(gids + j, c);
+#pragma unroll
+          for (int u = 0; u < UU; ++u) gather(c[u], x[u], as[u], dn[u]);
+          fwd_consume<SC, TRAIN, UU>(p, x, as, dn, UU, k0 + off + j, L, so, d_own, xi, st);
         }
       }
     } else {
       const int nbmax = __reduce_max_sync(FULLMASK, nb);
 #pragma unroll 1
-      for (int j = 0; j < nbmax; j += U) {
-        float4 x[U][2];
-        float as[U], dn[U];
+      for (int j = 0; j < nbmax; j += UU) {
+        float4 x[UU][2];
+        float as[UU], dn[UU];
+        uint32_t c[UU];
+        lds_ids<UU>(gids + (j & (G - 1)), c);
 #pragma unroll
-        for (int u = 0; u < U; ++u)                         // lanes past nb hold id 0: a valid row
-          gather((uint32_t)__shfl_sync(FULLMASK, cl, (j + u) & (G - 1), G), x[u], as[u], dn[u]);
+        for (int u = 0; u < UU; ++u) gather(c[u], x[u], as[u], dn[u]);
         int nv = nb - j;
-        nv = nv < 0 ? 0 : (nv > U ? U : nv);
-        fwd_consume<SC, TRAIN>(p, x, as, dn, nv, k0 + off + j, L, so, d_own, xi, st);
+        nv = nv < 0 ? 0 : (nv > UU ? UU : nv);
+        fwd_consume<SC, TRAIN, UU>(p, x, as, dn, nv, k0 + off + j, L, so, d_own, xi, st);
       }
     }
-    cl = cn;
   }
 }
 
@@ -326,8 +367,9 @@ __device__ __forceinline__ void fwd_init(FwdState& st) {
   st.acc[0] = st.acc[1] = st.acc2[0] = st.acc2[1] = zero4();
 }
 
-template <int SC, bool TRAIN, int G>
+template <int SC, bool TRAIN, int G, int UU, bool PIPE>
 __global__ void __launch_bounds__(ATT_THREADS, fwd_minb<SC, TRAIN>()) att_fwd_rows_kernel(const AttParams p) {
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   const int gl = threadIdx.x % G;
   int64_t row, k0, k1;
   const bool live = row_of_group(p, G, row, k0, k1);
@@ -341,7 +383,7 @@ __global__ void __launch_bounds__(ATT_THREADS, fwd_minb<SC, TRAIN>()) att_fwd_ro
   }
   FwdState st;
   fwd_init(st);
-  fwd_range<SC, TRAIN, G>(p, k0, k1, gl, L, so, d_own, xi, st);
+  fwd_range<SC, TRAIN, G, UU, PIPE>(p, k0, k1, gl, L, so, d_own, xi, sm_ids, st);
   if (!live || L.nact == 0) return;
   float inv = 1.0f;
   if constexpr (SC != SC_FA) inv = (k1 > k0) ? 1.0f / (st.s + 1e-16f) : 0.f;
@@ -367,10 +409,11 @@ __global__ void __launch_bounds__(ATT_THREADS, fwd_minb<SC, TRAIN>()) att_fwd_ro
 
 // long rows: one CTA per (work item, head tile); the CTA's Q groups take contiguous sub-ranges, their states
 // are merged through shared memory in group order
-template <int SC, bool TRAIN, int G>
+template <int SC, bool TRAIN, int G, int UU, bool PIPE>
 __global__ void __launch_bounds__(ATT_THREADS, fwd_minb<SC, TRAIN>()) att_fwd_long_kernel(const AttParams p) {
   constexpr int Q = ATT_THREADS / G;
   constexpr int W = G * 8;
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   __shared__ float sm_acc[Q * W];
   __shared__ float sm_acc2[TRAIN ? Q * W : 1];
   __shared__ float sm_m[Q][G], sm_s[Q][G], sm_q[Q][G];      // heads per tile <= lanes per group
@@ -385,7 +428,7 @@ __global__ void __launch_bounds__(ATT_THREADS, fwd_minb<SC, TRAIN>()) att_fwd_lo
   if constexpr (SC == SC_MX) load_own(p.Xo, p.ldo_, row, L, xi);
   FwdState st;
   fwd_init(st);
-  fwd_range<SC, TRAIN, G>(p, k0, k1, gl, L, so, d_own, xi, st);
+  fwd_range<SC, TRAIN, G, UU, PIPE>(p, k0, k1, gl, L, so, d_own, xi, sm_ids, st);
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     const bool act = v < L.nact;
@@ -549,37 +592,46 @@ att_bwd_prep_kernel(const float* __restrict__ dout, int64_t ldd, const float* __
 // ---- transpose pass: rows = sources j, neighbours = targets i -----------------------------------------------
 template <int SC, int G>
 __device__ __forceinline__ void bwdT_range(const AttParams& p, int64_t k0, int64_t k1, int gl, const Lane& L, float so2,
-                                           float d_own, const float4 (&xj)[2], float4 (&acc)[2], float& das) {
+                                           float d_own, const float4 (&xj)[2], int32_t* sm_ids, float4 (&acc)[2], float& das) {
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
   const int maxlen = __reduce_max_sync(FULLMASK, len);
   if (maxlen == 0) return;
   const int32_t* __restrict__ col = p.col + k0;
   const char* db0 = reinterpret_cast<const char*>(p.Xn + L.f);
-  const char* db1 = reinterpret_cast<const char*>(p.Xn + L.f + (L.nact > 1 ? 4 : 0));
+  const char* db1 = reinterpret_cast<const char*>(p.Xn + L.f + 4);
   const uint32_t d_bytes = (uint32_t)(p.ldn * 4);
   const char* xb0 = (SC == SC_MX) ? reinterpret_cast<const char*>(p.Xn2 + L.f) : nullptr;
-  const char* xb1 = (SC == SC_MX) ? reinterpret_cast<const char*>(p.Xn2 + L.f + (L.nact > 1 ? 4 : 0)) : nullptr;
+  const char* xb1 = (SC == SC_MX) ? reinterpret_cast<const char*>(p.Xn2 + L.f + 4) : nullptr;
   const uint32_t x_bytes = (uint32_t)(p.ldn2 * 4);
   const char* stb = reinterpret_cast<const char*>(p.stats + L.h);
   const uint32_t st_bytes = (uint32_t)(p.H * 16);
-  int32_t cl = (gl < len) ? __ldcs(col + gl) : 0;
+  const bool a0 = L.nact > 0, a1 = L.nact > 1;
+  const int lane = threadIdx.x & 31;
+  int32_t* wids = sm_ids + (threadIdx.x & ~31);
+  const int32_t* gids = wids + (lane - gl);
+  int32_t cn = (gl < len) ? __ldcs(col + gl) : 0;
   for (int off = 0; off < maxlen; off += G) {
     int nb = len - off;
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
-    int32_t cn = 0;
+    __syncwarp();
+    wids[lane] = cn;
+    __syncwarp();
+    cn = 0;
     if (off + G + gl < len) cn = __ldcs(col + off + G + gl);
     const int nbmax = __reduce_max_sync(FULLMASK, nb);
 #pragma unroll 1
     for (int j = 0; j < nbmax; j += U) {
       float4 d[U][2], x2[U][2], st[U];
+      uint32_t cc[U];
+      lds_ids<U>(gids + (j & (G - 1)), cc);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t ci = (uint32_t)__shfl_sync(FULLMASK, cl, (j + u) & (G - 1), G);
-        d[u][0] = __ldg(reinterpret_cast<const float4*>(db0 + (size_t)ci * d_bytes));
-        d[u][1] = __ldg(reinterpret_cast<const float4*>(db1 + (size_t)ci * d_bytes));
+        const uint32_t ci = cc[u];
+        d[u][0] = a0 ? __ldg(reinterpret_cast<const float4*>(db0 + (size_t)ci * d_bytes)) : zero4();
+        d[u][1] = a1 ? __ldg(reinterpret_cast<const float4*>(db1 + (size_t)ci * d_bytes)) : zero4();
         if constexpr (SC == SC_MX) {
-          x2[u][0] = __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)ci * x_bytes));
-          x2[u][1] = __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)ci * x_bytes));
+          x2[u][0] = a0 ? __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)ci * x_bytes)) : zero4();
+          x2[u][1] = a1 ? __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)ci * x_bytes)) : zero4();
         }
         st[u] = __ldg(reinterpret_cast<const float4*>(stb + (size_t)ci * st_bytes));
       }
@@ -619,7 +671,6 @@ __device__ __forceinline__ void bwdT_range(const AttParams& p, int64_t k0, int64
         }
       }
     }
-    cl = cn;
   }
 }
 
@@ -628,6 +679,7 @@ constexpr int bwdT_minb() { return SC == SC_MX ? 2 : 3; }
 
 template <int SC, int G>
 __global__ void __launch_bounds__(ATT_THREADS, bwdT_minb<SC>()) att_bwdT_rows_kernel(const AttParams p) {
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   const int gl = threadIdx.x % G;
   int64_t row, k0, k1;
   const bool live = row_of_group(p, G, row, k0, k1);
@@ -640,7 +692,7 @@ __global__ void __launch_bounds__(ATT_THREADS, bwdT_minb<SC>()) att_bwdT_rows_ke
     load_own(p.Xo, p.ldo_, row, L, xj);
   }
   float das = 0.f;
-  bwdT_range<SC, G>(p, k0, k1, gl, L, so2, d_own, xj, acc, das);
+  bwdT_range<SC, G>(p, k0, k1, gl, L, so2, d_own, xj, sm_ids, acc, das);
   if (!live || L.nact == 0) return;
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
@@ -689,6 +741,7 @@ __device__ __forceinline__ void bwd_long_merge(const AttParams& p, int gl, int q
 template <int SC, int G>
 __global__ void __launch_bounds__(ATT_THREADS, bwdT_minb<SC>()) att_bwdT_long_kernel(const AttParams p) {
   constexpr int Q = ATT_THREADS / G;
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   __shared__ float sm_acc[Q * G * 8];
   __shared__ float sm_s[Q][G];
   const int gl = threadIdx.x % G, q = threadIdx.x / G;
@@ -701,7 +754,7 @@ __global__ void __launch_bounds__(ATT_THREADS, bwdT_minb<SC>()) att_bwdT_long_ke
   float4 xj[2], acc[2] = {zero4(), zero4()};
   load_own(p.Xo, p.ldo_, row, L, xj);
   float das = 0.f;
-  bwdT_range<SC, G>(p, k0, k1, gl, L, so2, d_own, xj, acc, das);
+  bwdT_range<SC, G>(p, k0, k1, gl, L, so2, d_own, xj, sm_ids, acc, das);
   bwd_long_merge<G>(p, gl, q, L, acc, das, sm_acc, sm_s);
 }
 
@@ -727,32 +780,42 @@ __global__ void __launch_bounds__(256) att_bwd_combine_kernel(const AttParams p)
 //   dXf_i = sum_j dlogit_ij x_j ;  da_r[i] = sum_j draw_ij * s_ij
 template <int G>
 __device__ __forceinline__ void bwdF_range(const AttParams& p, int64_t k0, int64_t k1, int gl, const Lane& L, const float4 st_own,
-                                           const float4 (&xi)[2], const float4 (&di)[2], float4 (&acc)[2], float& dar) {
+                                           const float4 (&xi)[2], const float4 (&di)[2], int32_t* sm_ids, float4 (&acc)[2],
+                                           float& dar) {
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
   const int maxlen = __reduce_max_sync(FULLMASK, len);
   if (maxlen == 0) return;
   const int32_t* __restrict__ col = p.col + k0;
   const char* xb0 = reinterpret_cast<const char*>(p.Xn + L.f);
-  const char* xb1 = reinterpret_cast<const char*>(p.Xn + L.f + (L.nact > 1 ? 4 : 0));
+  const char* xb1 = reinterpret_cast<const char*>(p.Xn + L.f + 4);
   const uint32_t row_bytes = (uint32_t)(p.ldn * 4);
   const char* snb = reinterpret_cast<const char*>(p.sn + L.h);
   const uint32_t sn_bytes = (uint32_t)(p.H * 4);
-  int32_t cl = (gl < len) ? __ldcs(col + gl) : 0;
+  const bool a0 = L.nact > 0, a1 = L.nact > 1;
+  const int lane = threadIdx.x & 31;
+  int32_t* wids = sm_ids + (threadIdx.x & ~31);
+  const int32_t* gids = wids + (lane - gl);
+  int32_t cn = (gl < len) ? __ldcs(col + gl) : 0;
   for (int off = 0; off < maxlen; off += G) {
     int nb = len - off;
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
-    int32_t cn = 0;
+    __syncwarp();
+    wids[lane] = cn;
+    __syncwarp();
+    cn = 0;
     if (off + G + gl < len) cn = __ldcs(col + off + G + gl);
     const int nbmax = __reduce_max_sync(FULLMASK, nb);
 #pragma unroll 1
     for (int j = 0; j < nbmax; j += U) {
       float4 x[U][2];
       float as[U];
+      uint32_t cc[U];
+      lds_ids<U>(gids + (j & (G - 1)), cc);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const uint32_t cj = (uint32_t)__shfl_sync(FULLMASK, cl, (j + u) & (G - 1), G);
-        x[u][0] = __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)cj * row_bytes));
-        x[u][1] = __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)cj * row_bytes));
+        const uint32_t cj = cc[u];
+        x[u][0] = a0 ? __ldg(reinterpret_cast<const float4*>(xb0 + (size_t)cj * row_bytes)) : zero4();
+        x[u][1] = a1 ? __ldg(reinterpret_cast<const float4*>(xb1 + (size_t)cj * row_bytes)) : zero4();
         as[u] = __ldg(reinterpret_cast<const float*>(snb + (size_t)cj * sn_bytes));
       }
 #pragma unroll
@@ -772,12 +835,12 @@ __device__ __forceinline__ void bwdF_range(const AttParams& p, int64_t k0, int64
         }
       }
     }
-    cl = cn;
   }
 }
 
 template <int G>
 __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_rows_kernel(const AttParams p) {
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   const int gl = threadIdx.x % G;
   int64_t row, k0, k1;
   const bool live = row_of_group(p, G, row, k0, k1);
@@ -790,7 +853,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_rows_kernel(const Att
     st_own = __ldg(p.stats + row * p.H + L.h);
   }
   float dar = 0.f;
-  bwdF_range<G>(p, k0, k1, gl, L, st_own, xi, di, acc, dar);
+  bwdF_range<G>(p, k0, k1, gl, L, st_own, xi, di, sm_ids, acc, dar);
   if (!live || L.nact == 0) return;
 #pragma unroll
   for (int v = 0; v < 2; ++v)
@@ -801,6 +864,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_rows_kernel(const Att
 template <int G>
 __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_long_kernel(const AttParams p) {
   constexpr int Q = ATT_THREADS / G;
+  __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   __shared__ float sm_acc[Q * G * 8];
   __shared__ float sm_s[Q][G];
   const int gl = threadIdx.x % G, q = threadIdx.x / G;
@@ -812,7 +876,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_long_kernel(const Att
   load_own(p.Do, p.lddo, row, L, di);
   const float4 st_own = __ldg(p.stats + row * p.H + L.h);
   float dar = 0.f;
-  bwdF_range<G>(p, k0, k1, gl, L, st_own, xi, di, acc, dar);
+  bwdF_range<G>(p, k0, k1, gl, L, st_own, xi, di, sm_ids, acc, dar);
   bwd_long_merge<G>(p, gl, q, L, acc, dar, sm_acc, sm_s);
 }
 
@@ -889,24 +953,47 @@ static bool carve_split(AttParams& p, Carver& cv, int HC, int64_t n_items) {
 #define ATT_G_SWITCH(G_, CALL4, CALL8, CALL16) \
   switch (G_) { case 4: CALL4; break; case 8: CALL8; break; default: CALL16; break; }
 
-template <int SC, bool TRAIN>
-static int launch_fwd(const AttParams& p, const Shape& s, cudaStream_t st) {
+// forward loop variant: 0 = 2 edges per step, software-pipelined (round 1's shape); 1 = 4 edges per step, plain;
+// 2 = 2 edges per step, plain (default).  Measured on the Reddit-shaped 8x8 layer with the ids staged in shared
+// memory (profiles/r02_att_variants.txt): 3.27 / 2.77 / 2.50 ms -- the explicit pipeline now only costs registers
+// and issue slots.  RGBMP_ATT_FWD selects a variant for experiments.
+static int att_fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RGBMP_ATT_FWD");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
+  }
+  return v;
+}
+
+template <int SC, bool TRAIN, int UU, bool PIPE>
+static int launch_fwd_v(const AttParams& p, const Shape& s, cudaStream_t st) {
   const int HC = p.H * p.C;
   dim3 grid_rows((unsigned)ceil_div(p.n_rows, ATT_THREADS / s.G), (unsigned)s.tiles);
-  ATT_G_SWITCH(s.G, (att_fwd_rows_kernel<SC, TRAIN, 4><<<grid_rows, ATT_THREADS, 0, st>>>(p)),
-               (att_fwd_rows_kernel<SC, TRAIN, 8><<<grid_rows, ATT_THREADS, 0, st>>>(p)),
-               (att_fwd_rows_kernel<SC, TRAIN, 16><<<grid_rows, ATT_THREADS, 0, st>>>(p)))
+  ATT_G_SWITCH(s.G, (att_fwd_rows_kernel<SC, TRAIN, 4, UU, PIPE><<<grid_rows, ATT_THREADS, 0, st>>>(p)),
+               (att_fwd_rows_kernel<SC, TRAIN, 8, UU, PIPE><<<grid_rows, ATT_THREADS, 0, st>>>(p)),
+               (att_fwd_rows_kernel<SC, TRAIN, 16, UU, PIPE><<<grid_rows, ATT_THREADS, 0, st>>>(p)))
   RGBMP_LAUNCH_CHECK("att_fwd_rows_kernel");
   if (p.n_items > 0) {
     dim3 grid_items((unsigned)p.n_items, (unsigned)s.tiles);
-    ATT_G_SWITCH(s.G, (att_fwd_long_kernel<SC, TRAIN, 4><<<grid_items, ATT_THREADS, 0, st>>>(p)),
-                 (att_fwd_long_kernel<SC, TRAIN, 8><<<grid_items, ATT_THREADS, 0, st>>>(p)),
-                 (att_fwd_long_kernel<SC, TRAIN, 16><<<grid_items, ATT_THREADS, 0, st>>>(p)))
+    ATT_G_SWITCH(s.G, (att_fwd_long_kernel<SC, TRAIN, 4, UU, PIPE><<<grid_items, ATT_THREADS, 0, st>>>(p)),
+                 (att_fwd_long_kernel<SC, TRAIN, 8, UU, PIPE><<<grid_items, ATT_THREADS, 0, st>>>(p)),
+                 (att_fwd_long_kernel<SC, TRAIN, 16, UU, PIPE><<<grid_items, ATT_THREADS, 0, st>>>(p)))
     RGBMP_LAUNCH_CHECK("att_fwd_long_kernel");
     att_fwd_combine_kernel<SC, TRAIN><<<(unsigned)ceil_div(p.n_long * HC, 256), 256, 0, st>>>(p);
     RGBMP_LAUNCH_CHECK("att_fwd_combine_kernel");
   }
   return 0;
+}
+
+template <int SC, bool TRAIN>
+static int launch_fwd(const AttParams& p, const Shape& s, cudaStream_t st) {
+  switch (att_fwd_variant()) {
+    case 1: return launch_fwd_v<SC, TRAIN, 4, false>(p, s, st);
+    case 0: return launch_fwd_v<SC, TRAIN, 2, true>(p, s, st);
+    default: return launch_fwd_v<SC, TRAIN, 2, false>(p, s, st);
+  }
 }
 
 template <int SC>

@@ -647,27 +647,32 @@ __global__ void longrow_count_kernel(const int64_t* __restrict__ rowptr, int64_t
   }
 }
 
+// position p of the list order <-> row order[p] (order == NULL: natural order).  Listing the long rows in the
+// order of the row schedule keeps the work items of one locality group adjacent in the long-row launch.
 __global__ void longrow_flags_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk,
-                                     int32_t long_chunk, int32_t* __restrict__ slot, int32_t* __restrict__ items) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows) return;
+                                     int32_t long_chunk, const int32_t* __restrict__ order, int32_t* __restrict__ slot,
+                                     int32_t* __restrict__ items) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_rows) return;
+  const int64_t i = order ? order[p] : p;
   const int64_t deg = rowptr[i + 1] - rowptr[i];
   const bool lg = deg > chunk;
-  slot[i] = lg ? 1 : 0;
-  items[i] = lg ? (int32_t)((deg + long_chunk - 1) / long_chunk) : 0;
+  slot[p] = lg ? 1 : 0;
+  items[p] = lg ? (int32_t)((deg + long_chunk - 1) / long_chunk) : 0;
 }
 
 __global__ void longrow_fill_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t chunk,
-                                    int32_t long_chunk, const int32_t* __restrict__ slot,
+                                    int32_t long_chunk, const int32_t* __restrict__ order, const int32_t* __restrict__ slot,
                                     const int32_t* __restrict__ items, int64_t n_long, int64_t n_items,
                                     int32_t* __restrict__ long_rows, int32_t* __restrict__ long_item_ptr,
                                     int32_t* __restrict__ item_long, int64_t* __restrict__ item_start) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) long_item_ptr[n_long] = (int32_t)n_items;
-  if (i >= n_rows) return;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) long_item_ptr[n_long] = (int32_t)n_items;
+  if (p >= n_rows) return;
+  const int64_t i = order ? order[p] : p;
   const int64_t s = rowptr[i], deg = rowptr[i + 1] - s;
   if (deg <= chunk) return;
-  const int32_t sl = slot[i], it0 = items[i];
+  const int32_t sl = slot[p], it0 = items[p];
   long_rows[sl] = (int32_t)i;
   long_item_ptr[sl] = it0;
   const int32_t cnt = (int32_t)((deg + long_chunk - 1) / long_chunk);
@@ -755,12 +760,13 @@ static int sort_csr_packed(const int32_t* key, const int32_t* other, int64_t n, 
 }
 
 __global__ void row_key_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t window,
-                               int32_t* __restrict__ keys) {
+                               const int32_t* __restrict__ group, int32_t* __restrict__ keys) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   int64_t deg = rowptr[i + 1] - rowptr[i];
   if (deg > 0xFFFF) deg = 0xFFFF;
-  keys[i] = (int32_t)(((i / window) << 16) | (0xFFFF - deg));   // window-major, longest rows first
+  const int64_t major = group ? (int64_t)group[i] : i / window;   // locality group, or window of consecutive ids
+  keys[i] = (int32_t)((major << 16) | (0xFFFF - deg));            // major first, longest rows first inside
 }
 
 __global__ void __launch_bounds__(256)
@@ -1004,6 +1010,14 @@ size_t rgbmp_longrow_fill_workspace_bytes(int64_t n_rows) {
 int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk, int64_t n_long,
                        int64_t n_items, int32_t* long_rows, int32_t* long_item_ptr, int32_t* item_long,
                        int64_t* item_start, void* ws, size_t ws_bytes, int device, void* stream) {
+  return rgbmp_longrow_fill_ordered(rowptr, n_rows, chunk, long_chunk, nullptr, n_long, n_items, long_rows, long_item_ptr,
+                                    item_long, item_start, ws, ws_bytes, device, stream);
+}
+
+int rgbmp_longrow_fill_ordered(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int32_t long_chunk,
+                               const int32_t* order, int64_t n_long, int64_t n_items, int32_t* long_rows,
+                               int32_t* long_item_ptr, int32_t* item_long, int64_t* item_start, void* ws, size_t ws_bytes,
+                               int device, void* stream) {
   if (!rowptr || n_rows <= 0 || n_long <= 0 || n_items <= 0 || !long_rows || !long_item_ptr || !item_long ||
       !item_start || !ws)
     return fail(RGBMP_EINVAL, "rgbmp_longrow_fill: bad argument");
@@ -1016,11 +1030,11 @@ int rgbmp_longrow_fill(const int64_t* rowptr, int64_t n_rows, int32_t chunk, int
   int32_t* items = cv.take<int32_t>((size_t)n_rows);
   int32_t* sc = cv.take<int32_t>(scan_ws_elems(n_rows));
   const unsigned nb = (unsigned)ceil_div(n_rows, 256);
-  longrow_flags_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, slot, items);
+  longrow_flags_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, order, slot, items);
   RGBMP_LAUNCH_CHECK("longrow_flags_kernel");
   RGBMP_CUDA(exclusive_scan<int32_t>(slot, n_rows, sc, st));
   RGBMP_CUDA(exclusive_scan<int32_t>(items, n_rows, sc, st));
-  longrow_fill_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, slot, items, n_long, n_items, long_rows,
+  longrow_fill_kernel<<<nb, 256, 0, st>>>(rowptr, n_rows, chunk, long_chunk, order, slot, items, n_long, n_items, long_rows,
                                           long_item_ptr, item_long, item_start);
   RGBMP_LAUNCH_CHECK("longrow_fill_kernel");
   return 0;
@@ -1035,14 +1049,20 @@ size_t rgbmp_row_order_workspace_bytes(int64_t n_rows) {
 
 int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32_t* order, void* ws, size_t ws_bytes,
                     int device, void* stream) {
-  if (!rowptr || !order || n_rows <= 0 || window <= 0 || !ws) return fail(RGBMP_EINVAL, "rgbmp_row_order: bad argument");
+  return rgbmp_row_order_grouped(rowptr, n_rows, window, nullptr, 0, order, ws, ws_bytes, device, stream);
+}
+
+int rgbmp_row_order_grouped(const int64_t* rowptr, int64_t n_rows, int64_t window, const int32_t* group, int32_t n_groups,
+                            int32_t* order, void* ws, size_t ws_bytes, int device, void* stream) {
+  if (!rowptr || !order || n_rows <= 0 || (!group && window <= 0) || !ws) return fail(RGBMP_EINVAL, "rgbmp_row_order: bad argument");
+  if (group && (n_groups <= 0 || n_groups > 32768)) return fail(RGBMP_ERANGE, "rgbmp_row_order: n_groups must be in 1..32768");
   if (n_rows >= (1ll << 31) - 1) return fail(RGBMP_ERANGE, "rgbmp_row_order: n_rows exceeds int32");
   if (ws_bytes < rgbmp_row_order_workspace_bytes(n_rows)) return fail(RGBMP_EWORKSPACE, "rgbmp_row_order: workspace");
   DeviceGuard dg(device);
   if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_row_order: bad device");
   cudaStream_t st = (cudaStream_t)stream;
-  if (window < ceil_div(n_rows, 32768)) window = ceil_div(n_rows, 32768);   // window id must fit 15 bits
-  const int64_t nwin = ceil_div(n_rows, window);
+  if (!group && window < ceil_div(n_rows, 32768)) window = ceil_div(n_rows, 32768);   // window id must fit 15 bits
+  const int64_t nwin = group ? (int64_t)n_groups : ceil_div(n_rows, window);
   int wbits = 0;
   while ((1ll << wbits) < nwin) ++wbits;
   const int64_t nb = ceil_div(n_rows, RS_TILE);
@@ -1054,7 +1074,7 @@ int rgbmp_row_order(const int64_t* rowptr, int64_t n_rows, int64_t window, int32
   int32_t* bh = cv.take<int32_t>((size_t)RS_BINS * nb);
   int32_t* sc32 = cv.take<int32_t>(scan_ws_elems(RS_BINS * nb));
   if (!cv.ok()) return fail(RGBMP_EWORKSPACE, "rgbmp_row_order: workspace carve");
-  row_key_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, window, keys);
+  row_key_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(rowptr, n_rows, group ? 1 : window, group, keys);
   RGBMP_LAUNCH_CHECK("row_key_kernel");
   return sort_pairs_i32(keys, n_rows, 16 + wbits, kA, kB, vA, order, bh, sc32, nb, st);
 }

@@ -30,29 +30,26 @@ pack_rows_kernel(const float* __restrict__ X, int64_t ld, float* __restrict__ Y,
   }
 }
 
-// choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 with the v2 kernel and the
-// global degree-sorted row schedule (tools/sweep.py, profiles/r01_sweep_v2.txt):
-//   * two vectors per lane (V = 2) on half as many lanes beat V = 1 once the gathers come from HBM
-//     (products F=47: G8 V2 3.48 ms vs G16 V1 3.66 ms; F=100: G16 V2 7.06 vs G32 V1 7.64);
-//   * when the feature matrix is L2-resident (arxiv F=40 / bf16 F=128) V = 1 with 4 pipelined
-//     edges wins (0.148 vs 0.224 ms);
-//   * the software-pipelined loop (U = 18 / 20) wins nearly everywhere; V >= 3 and U = 8 never do;
-//   * rows wider than 64 vectors are tiled over blockIdx.y with G = 32, V = 2.
+// choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 with the round-2 inner loop (column ids
+// staged through shared memory, lanes beyond F issue no load; tools/sweep.py, profiles/r02_sweep.txt):
+//   * one vector per lane with 8 plain (not software-pipelined) edges in flight wins wherever a row fits 16 lanes --
+//     products F=47 3.03 ms (G16 V1 U8) vs 3.64 (round 1's G8 V2 pipelined), F=64 3.04 vs 3.84, arxiv F=40 0.116 vs
+//     0.156, bf16 F=128 0.129 vs 0.165, reddit F=64 1.51 vs 1.89 -- both when the gathers come from HBM and when
+//     they are L2-resident: with the id broadcast out of the LSU data pipe, fewer and fuller wavefronts per edge
+//     beat deeper per-lane pipelines;
+//   * wider rows take two vectors per lane with 4 edges in flight (F=100: G16 V2 U4 6.02 vs 7.05; F=256: G32 V2
+//     U4 0.307 vs 0.459); rows wider than 64 vectors are tiled over blockIdx.y;
+//   * narrow rows: 8 lanes x 8 edges for 5-8 vectors (F=24/32: 1.81 / 1.74 ms), 4 lanes below that -- pipelined
+//     for 1-2 vectors, where two idle lanes still beat the 2-lane group (F=8: 0.86 vs 1.08 ms).
 static void choose_shape(int nvec, bool hbm_regime, int* G, int* V, int* U) {
-  if (nvec > 32) { *G = 32; *V = 2; *U = 20; return; }
-  if (nvec > 16) { *G = 16; *V = 2; *U = 18; return; }
-  if (nvec > 8) {
-    if (hbm_regime) { *G = 8; *V = 2; *U = 18; }
-    else { *G = 16; *V = 1; *U = 20; }
-    return;
-  }
-  // narrow rows (products-shaped sweep at F = 8/16/24/32, profiles/r01_sweep_narrow.txt): 8 lanes with 4
-  // plain edges in flight for 5-8 vectors (F=24: 2.22 vs 2.50 ms pipelined), 4 lanes pipelined below
-  // that -- even for 1-2 vectors, where two idle lanes beat the 2-lane group (F=8: 1.33 vs 2.03 ms)
-  if (nvec > 4) { *G = 8; *V = 1; *U = 4; return; }
+  (void)hbm_regime;
+  if (nvec > 32) { *G = 32; *V = 2; *U = 4; return; }
+  if (nvec > 16) { *G = 16; *V = 2; *U = 4; return; }
+  if (nvec > 8) { *G = 16; *V = 1; *U = 8; return; }
+  if (nvec > 4) { *G = 8; *V = 1; *U = 8; return; }
   *G = 4;
   *V = 1;
-  *U = 20;
+  *U = nvec > 2 ? 4 : 20;
 }
 
 static int check_graph(const rgbmp_graph_t* g, const char* fn) {
@@ -144,7 +141,7 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
     V = (tune >> 8) & 0xFF;
     U = (tune >> 16) & 0xFF;
     const bool pow2 = G > 0 && (G & (G - 1)) == 0 && G <= 32;
-    if (!pow2 || V < 1 || V > 2 || (U != 2 && U != 4 && U != 18 && U != 20))
+    if (!pow2 || V < 1 || V > 2 || (U != 2 && U != 4 && U != 8 && U != 18 && U != 20))
       return fail(RGBMP_EINVAL, "rgbmp_spmm: bad tune word 0x%x", tune);
   }
   if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(p, G, V, U, st);

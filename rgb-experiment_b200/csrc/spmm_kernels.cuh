@@ -204,27 +204,74 @@ __device__ __forceinline__ uint64_t make_policy(int kind) {
 // The L2 policy travels in a memory DESCRIPTOR, which is warp-uniform on sm_100 (ptxas moves a
 // per-lane policy through R2UR, i.e. silently applies one lane's choice to the whole warp), so the
 // choice is expressed as two predicated loads with kernel-uniform policies.
+// `act` = this lane owns an existing vector of the row (lane-constant): lanes beyond F issue NO load -- a
+// predicated-off lane costs nothing in the LSU, while a dummy load of vector 0 touched a second cache line per
+// gathered row (one more L1 wavefront and two more sectors per edge for F = 47; profiles/r02_spmm_l1_wavefronts.txt).
 template <typename T, int EPV>
 __device__ __forceinline__ void gather_vec(Raw<T, EPV>& raw, const char* base, uint32_t ctag, uint32_t row_bytes,
-                                           uint64_t pol_hot, uint64_t pol_cold) {
+                                           uint64_t pol_hot, uint64_t pol_cold, bool act) {
   const T* q = reinterpret_cast<const T*>(row_addr(base, ctag & 0x7fffffffu, row_bytes));
-  if (ctag & 0x80000000u) raw.load_hint(q, pol_hot);
+  if (!act) raw.zero();
+  else if (ctag & 0x80000000u) raw.load_hint(q, pol_hot);
   else raw.load_hint(q, pol_cold);
+}
+
+// Column ids (and weights) of a batch reach the lanes of a group through SHARED MEMORY: each lane loads one id
+// with a coalesced streaming load, the warp stores its 32 ids to its own 128-byte slot, and every lane then reads
+// the UE ids of a step with ONE broadcast LDS (8 lanes of a group read the same address, the 4 groups of a warp
+// 4 different ones: one wavefront).  The round-1 kernel broadcast each id with a warp shuffle; on sm_100 a SHFL
+// occupies the LSU data pipe for 4 wavefronts, and with the gathers L2-resident that pipe is the limiter
+// (l1tex__data_pipe_lsu_wavefronts 74 % busy, 37 % of it shuffles; profiles/r02_spmm_l1_wavefronts.txt).
+struct IdStage {
+  int32_t* ids;     // this warp's 32 ids   (shared memory)
+  float* wts;       // this warp's 32 weights
+};
+
+template <int N>
+__device__ __forceinline__ void lds_ids(const int32_t* p, uint32_t (&c)[N]) {
+  if constexpr (N == 8) {
+    const int4 v = *reinterpret_cast<const int4*>(p), w = *reinterpret_cast<const int4*>(p + 4);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; c[4] = w.x; c[5] = w.y; c[6] = w.z; c[7] = w.w;
+  } else if constexpr (N == 4) {
+    const int4 v = *reinterpret_cast<const int4*>(p);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+  } else if constexpr (N == 2) {
+    const int2 v = *reinterpret_cast<const int2*>(p);
+    c[0] = v.x; c[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = p[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void lds_wts(const float* p, float (&w)[N]) {
+  if constexpr (N == 8) {
+    const float4 v = *reinterpret_cast<const float4*>(p), x = *reinterpret_cast<const float4*>(p + 4);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; w[4] = x.x; w[5] = x.y; w[6] = x.z; w[7] = x.w;
+  } else if constexpr (N == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else if constexpr (N == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    w[0] = v.x; w[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = p[i];
+  }
 }
 
 // The loop is WARP-uniform: every lane of the warp runs the same number of batches (the maximum
 // over the warp's groups; with the degree-sorted row schedule the groups of a warp have equal
-// lengths, so nothing is wasted), which lets all shuffles use the full mask (no convergence
-// checks) and lets full batches run without a single predicate.
-// xb[v]: this lane's base pointer for its v-th vector (lanes beyond F point at vector 0 of the
-// row -- they load valid memory and never store).
+// lengths, so nothing is wasted), which lets full batches run without a single predicate.
+// xb[v]: this lane's base pointer for its v-th vector; active[v]: the vector exists (lane-constant).
 // PIPE: software-pipelined main loop -- the features of step j+1 are requested BEFORE the math of
 // step j and consumed in the next loop iteration, so UE*V loads per lane are always in flight
 // whatever order ptxas picks inside one iteration (without it, ptxas 12.9 sinks each LDG next to
 // its FFMA2 and serialises the gathers).
 template <typename T, int EPV, int G, int V, int U, bool HASW, bool PIPE>
 __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0, int64_t k1, const char* const (&xb)[V],
-                                                 int gl, float2 (&acc)[V][(EPV + 1) / 2]) {
+                                                 const bool (&active)[V], int gl, const IdStage& sm,
+                                                 float2 (&acc)[V][(EPV + 1) / 2]) {
   constexpr int UE = (U < G) ? U : G;   // edges per inner step (a batch holds G ids)
   const uint32_t row_bytes = (uint32_t)(p.ldx * (int64_t)sizeof(T));
   const uint64_t pol_hot = make_policy(p.pol_hot), pol_cold = make_policy(p.pol_cold);
@@ -233,14 +280,21 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;          // <= chunk / long sub-range, fits int
   const int maxlen = __reduce_max_sync(FULL, len);
   if (maxlen == 0) return;
-  int32_t cl = (gl < len) ? ld_stream(col + gl, p.stream) : 0;
-  float wl = 0.f;
-  if constexpr (HASW) wl = (gl < len) ? ld_stream(val + gl, p.stream) : 0.f;
+  const int lane = threadIdx.x & 31;
+  const int32_t* gid_ = sm.ids + (lane - gl);              // this group's G slots
+  const float* gwt_ = sm.wts + (lane - gl);
+  int32_t cn = (gl < len) ? ld_stream(col + gl, p.stream) : 0;   // lanes past the row hold id 0: a valid row
+  float wn = 0.f;
+  if constexpr (HASW) wn = (gl < len) ? ld_stream(val + gl, p.stream) : 0.f;
   for (int off = 0; off < maxlen; off += G) {
     int nb = len - off;
     nb = nb < 0 ? 0 : (nb > G ? G : nb);
-    int32_t cn = 0;
-    float wn = 0.f;
+    __syncwarp();                                   // everybody has read the previous batch
+    sm.ids[lane] = cn;
+    if constexpr (HASW) sm.wts[lane] = wn;
+    __syncwarp();
+    cn = 0;
+    wn = 0.f;
     if (off + G + gl < len) {                       // prefetch the next batch of ids / weights
       cn = ld_stream(col + off + G + gl, p.stream);
       if constexpr (HASW) wn = ld_stream(val + off + G + gl, p.stream);
@@ -248,28 +302,30 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
     if (__all_sync(FULL, nb == G)) {                // every group has a full batch: no predicates
       if constexpr (PIPE && (G / UE) >= 2) {
         Raw<T, EPV> cur[UE][V];
+        {
+          uint32_t c[UE];
+          lds_ids<UE>(gid_, c);
 #pragma unroll
-        for (int u = 0; u < UE; ++u) {
-          const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, u, G);
+          for (int u = 0; u < UE; ++u)
 #pragma unroll
-          for (int v = 0; v < V; ++v) gather_vec<T, EPV>(cur[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(cur[u][v], xb[v], c[u], row_bytes, pol_hot, pol_cold, active[v]);
         }
 #pragma unroll 1
         for (int j = 0; j < G; j += UE) {
           Raw<T, EPV> nxt[UE][V];
           const int jn = (j + UE < G) ? j + UE : j;   // last step re-requests itself (L1 hit, result unused)
+          uint32_t c[UE];
+          lds_ids<UE>(gid_ + jn, c);
+#pragma unroll
+          for (int u = 0; u < UE; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(nxt[u][v], xb[v], c[u], row_bytes, pol_hot, pol_cold, active[v]);
+          float w[UE];
+          if constexpr (HASW) lds_wts<UE>(gwt_ + j, w);
 #pragma unroll
           for (int u = 0; u < UE; ++u) {
-            const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, jn + u, G);
 #pragma unroll
-            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(nxt[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
-          }
-#pragma unroll
-          for (int u = 0; u < UE; ++u) {
-            float w = 1.0f;
-            if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
-#pragma unroll
-            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], cur[u][v], w);
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], cur[u][v], HASW ? w[u] : 1.0f);
           }
 #pragma unroll
           for (int u = 0; u < UE; ++u)
@@ -280,18 +336,18 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
 #pragma unroll 1
         for (int j = 0; j < G; j += UE) {
           Raw<T, EPV> raw[UE][V];
+          uint32_t c[UE];
+          lds_ids<UE>(gid_ + j, c);
+#pragma unroll
+          for (int u = 0; u < UE; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(raw[u][v], xb[v], c[u], row_bytes, pol_hot, pol_cold, active[v]);
+          float w[UE];
+          if constexpr (HASW) lds_wts<UE>(gwt_ + j, w);
 #pragma unroll
           for (int u = 0; u < UE; ++u) {
-            const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);
 #pragma unroll
-            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(raw[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
-          }
-#pragma unroll
-          for (int u = 0; u < UE; ++u) {
-            float w = 1.0f;
-            if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
-#pragma unroll
-            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], w);
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], HASW ? w[u] : 1.0f);
           }
         }
       }
@@ -300,27 +356,25 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
 #pragma unroll 1
       for (int j = 0; j < nbmax; j += UE) {
         Raw<T, EPV> raw[UE][V];
+        uint32_t c[UE];
+        lds_ids<UE>(gid_ + j, c);
 #pragma unroll
         for (int u = 0; u < UE; ++u) {
-          const uint32_t c = (uint32_t)__shfl_sync(FULL, cl, j + u, G);   // lanes past nb hold id 0: a valid row
-          if (j + u < nb) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) gather_vec<T, EPV>(raw[u][v], xb[v], c, row_bytes, pol_hot, pol_cold);
-          }
+          for (int v = 0; v < V; ++v)
+            gather_vec<T, EPV>(raw[u][v], xb[v], c[u], row_bytes, pol_hot, pol_cold, active[v] && (j + u < nb));
         }
+        float w[UE];
+        if constexpr (HASW) lds_wts<UE>(gwt_ + j, w);
 #pragma unroll
         for (int u = 0; u < UE; ++u) {
-          float w = 1.0f;
-          if constexpr (HASW) w = __shfl_sync(FULL, wl, j + u, G);
           if (j + u < nb) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], w);
+            for (int v = 0; v < V; ++v) accum_vec<T, EPV, HASW>(acc[v], raw[u][v], HASW ? w[u] : 1.0f);
           }
         }
       }
     }
-    cl = cn;
-    wl = wn;
   }
 }
 
@@ -390,7 +444,7 @@ __device__ __forceinline__ void lane_bases(const SpmmParams& p, int f0, const ch
   for (int v = 0; v < V; ++v) {
     const int f = f0 + v * G * EPV;
     active[v] = f < p.F;
-    xb[v] = reinterpret_cast<const char*>(p.X) + (size_t)(active[v] ? f : 0) * sizeof(T);
+    xb[v] = reinterpret_cast<const char*>(p.X) + (size_t)(active[v] ? f : 0) * sizeof(T);   // inactive: never dereferenced
   }
 }
 
@@ -419,7 +473,10 @@ __global__ void __launch_bounds__(SPMM_THREADS, spmm_minb<EPV, V, U, PIPE>()) sp
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int i = 0; i < (EPV + 1) / 2; ++i) acc[v][i] = make_float2(0.f, 0.f);
-  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, gl, acc);
+  __shared__ __align__(16) int32_t sm_ids[SPMM_THREADS];
+  __shared__ __align__(16) float sm_wts[HASW ? SPMM_THREADS : 4];
+  const IdStage stage = {sm_ids + (threadIdx.x & ~31), sm_wts + (HASW ? (threadIdx.x & ~31) : 0)};
+  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, active, gl, stage, acc);
   if (row < 0 || (p.ep.skip_empty && k1 == k0)) return;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -461,7 +518,10 @@ __global__ void __launch_bounds__(SPMM_THREADS, spmm_minb<EPV, V, U, PIPE>()) sp
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int i = 0; i < (EPV + 1) / 2; ++i) acc[v][i] = make_float2(0.f, 0.f);
-  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, gl, acc);
+  __shared__ __align__(16) int32_t sm_ids[SPMM_THREADS];
+  __shared__ __align__(16) float sm_wts[HASW ? SPMM_THREADS : 4];
+  const IdStage stage = {sm_ids + (threadIdx.x & ~31), sm_wts + (HASW ? (threadIdx.x & ~31) : 0)};
+  accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, active, gl, stage, acc);
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
@@ -539,6 +599,7 @@ template <typename T, int EPV, int G, int V>
 int dispatch_u(const SpmmParams& p, int U, cudaStream_t st) {
   switch (U) {
     case 2: return dispatch_w<T, EPV, G, V, 2, false>(p, st);
+    case 8: return dispatch_w<T, EPV, G, V, 8, false>(p, st);
     case 18: return dispatch_w<T, EPV, G, V, 2, true>(p, st);
     case 20: return dispatch_w<T, EPV, G, V, 4, true>(p, st);
     default: return dispatch_w<T, EPV, G, V, 4, false>(p, st);

@@ -28,6 +28,16 @@ DEFAULT_LONG_CHUNK = 4096   # ... into CTA work items of this many edges
 HOT_L2_BYTES = 64 << 20     # L2 budget for the hot (most gathered) feature rows; 0 turns the tagging off
 DEFAULT_WINDOW = -1         # row schedule: -1 = global degree sort (fastest on B200, profiles/r01_sweep_v2.txt),
                             # w > 0 = degree-sorted inside windows of w rows, 0 = natural order
+# Locality groups (csrc/cluster.cu): on graphs whose feature matrix will not fit L2 the rows are scheduled community
+# by community -- (group rank, -degree) -- so that the rows in flight gather from one L2-resident slice.
+CLUSTER = os.environ.get("RGBMP_CLUSTER", "auto")      # auto | 0 | 1
+CLUSTER_MIN_NODES = 200_000     # auto: below this every realistic feature matrix is L2-resident anyway
+CLUSTER_MIN_DEGREE = 4.0        # auto: mean degree below which a community's slice is not re-used enough to matter
+CLUSTER_SEEDS = 1024
+CLUSTER_TAUS = (0.3, 0.15, 0.05, 0.0, 0.0, 0.0)
+CLUSTER_MIN_INTRA = 0.25        # share of edges inside a group below which the graph has no community structure to use
+                                # (a uniform random graph still reaches ~0.15: every node shares a group with the neighbour it copied)
+cluster_stats = {"built": 0, "used": 0, "last": None}
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -39,7 +49,8 @@ class CSR:
     (position in the edited edge list), plus the long-row work lists and the ctypes descriptor."""
 
     def __init__(self, key: torch.Tensor, other: torch.Tensor, n_rows: int, n_cols: int,
-                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None):
+                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None,
+                 groups=None, finish: bool = True):
         L = lib()
         dev = key.device
         st = stream_of(dev)
@@ -53,7 +64,8 @@ class CSR:
         check(L.rgbmp_csr_build(ptr(key), ptr(other), nnz, n_rows, ptr(self.rowptr), ptr(self.col), ptr(self.eid),
                                 ptr(ws), ws.numel(), dev.index, st), "csr_build")
         self.col, self.eid = self.col[:nnz], self.eid[:nnz]
-        self._finish(chunk, long_chunk, window)
+        if finish:
+            self._finish(chunk, long_chunk, window, groups)
 
     @classmethod
     def from_arrays(cls, rowptr: torch.Tensor, col: torch.Tensor, n_cols: int, chunk: int = DEFAULT_CHUNK,
@@ -71,23 +83,44 @@ class CSR:
         self._finish(chunk, long_chunk, window)
         return self
 
-    def _finish(self, chunk: int, long_chunk: int, window: Optional[int]):
+    def degree_order(self) -> torch.Tensor:
+        """int32 [n_rows]: rows by degree, longest first (stable) -- the default schedule and the seed ranking."""
+        L = lib()
+        order = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
+        ws = _ws(L.rgbmp_row_order_workspace_bytes(self.n_rows), self.device)
+        check(L.rgbmp_row_order(ptr(self.rowptr), self.n_rows, self.n_rows, ptr(order), ptr(ws), ws.numel(),
+                                self.device.index, stream_of(self.device)), "row_order")
+        return order
+
+    def _finish(self, chunk: int, long_chunk: int, window: Optional[int], groups=None, deg_order=None):
+        """Row schedule, long-row work lists, descriptor.  groups = (group int32 [n_rows], n_groups): schedule by
+        (group, -degree) and list the long rows in that order too (locality groups, see Graph)."""
         L = lib()
         dev, n_rows, nnz = self.device, self.n_rows, self.nnz
         st = stream_of(dev)
         self.chunk, self.long_chunk = int(chunk), int(long_chunk)
         self.n_long = self.n_items = 0
         self.long_rows = self.long_item_ptr = self.item_long = self.item_start = None
-        self._split_long_rows()
         self.row_order = None
+        self.clustered = groups is not None
         window = DEFAULT_WINDOW if window is None else int(window)
         if window < 0:
             window = n_rows
-        if window > 0 and n_rows > 1 and nnz > 0:
-            self.row_order = torch.empty(n_rows, dtype=torch.int32, device=dev)
-            ws = _ws(L.rgbmp_row_order_workspace_bytes(n_rows), dev)
-            check(L.rgbmp_row_order(ptr(self.rowptr), n_rows, window, ptr(self.row_order), ptr(ws), ws.numel(),
-                                    dev.index, st), "row_order")
+        if n_rows > 1 and nnz > 0:
+            if groups is not None:
+                grp, n_groups = groups
+                self.row_order = torch.empty(n_rows, dtype=torch.int32, device=dev)
+                ws = _ws(L.rgbmp_row_order_workspace_bytes(n_rows), dev)
+                check(L.rgbmp_row_order_grouped(ptr(self.rowptr), n_rows, n_rows, ptr(grp), int(n_groups), ptr(self.row_order),
+                                                ptr(ws), ws.numel(), dev.index, st), "row_order_grouped")
+            elif window >= n_rows and deg_order is not None:
+                self.row_order = deg_order
+            elif window > 0:
+                self.row_order = torch.empty(n_rows, dtype=torch.int32, device=dev)
+                ws = _ws(L.rgbmp_row_order_workspace_bytes(n_rows), dev)
+                check(L.rgbmp_row_order(ptr(self.rowptr), n_rows, window, ptr(self.row_order), ptr(ws), ws.numel(),
+                                        dev.index, st), "row_order")
+        self._split_long_rows(self.row_order if self.clustered else None)
         self._norm = {}
         self._tagged = {}
         self.struct = self._make_struct(self.col, 0)
@@ -113,8 +146,8 @@ class CSR:
         bytes, or the plain descriptor when the whole feature matrix fits the L2 budget anyway.
         The hot set = the most frequently gathered rows that fit HOT_L2_BYTES; built once per
         row size class and cached."""
-        if HOT_L2_BYTES <= 0 or self.nnz == 0 or self.n_cols * row_bytes <= HOT_L2_BYTES:
-            return self.ref
+        if HOT_L2_BYTES <= 0 or self.nnz == 0 or self.n_cols * row_bytes <= HOT_L2_BYTES or self.clustered:
+            return self.ref        # a locality-grouped schedule keeps its own working set in L2: pinning the global hubs costs it room
         k_hot = max(1, HOT_L2_BYTES // max(row_bytes, 1))
         hit = self._tagged.get(k_hot)
         if hit is None:
@@ -129,7 +162,7 @@ class CSR:
             self._tagged[k_hot] = hit
         return hit[2]
 
-    def _split_long_rows(self):
+    def _split_long_rows(self, order=None):
         L = lib()
         dev, st = self.device, stream_of(self.device)
         if self.n_rows == 0 or self.nnz == 0:
@@ -146,9 +179,9 @@ class CSR:
         self.item_long = torch.empty(n_items, dtype=torch.int32, device=dev)
         self.item_start = torch.empty(n_items, dtype=torch.int64, device=dev)
         ws = _ws(L.rgbmp_longrow_fill_workspace_bytes(self.n_rows), dev)
-        check(L.rgbmp_longrow_fill(ptr(self.rowptr), self.n_rows, self.chunk, self.long_chunk, n_long, n_items,
-                                   ptr(self.long_rows), ptr(self.long_item_ptr), ptr(self.item_long),
-                                   ptr(self.item_start), ptr(ws), ws.numel(), dev.index, st), "longrow_fill")
+        check(L.rgbmp_longrow_fill_ordered(ptr(self.rowptr), self.n_rows, self.chunk, self.long_chunk, ptr(order), n_long,
+                                           n_items, ptr(self.long_rows), ptr(self.long_item_ptr), ptr(self.item_long),
+                                           ptr(self.item_start), ptr(ws), ws.numel(), dev.index, st), "longrow_fill")
 
     def norm(self, mode: int) -> torch.Tensor:
         """Per-row vector from the degree: deg^-1/2 | 1/max(deg,1) | max(deg,1)."""
@@ -167,6 +200,79 @@ class CSR:
         if self.n_items == 0:
             return None
         return _ws(self.n_items * ((F + 3) // 4 * 4) * 4 + 256, self.device)
+
+
+def chain_groups(W) -> "tuple":
+    """Linear order of the groups in which strongly connected ones are adjacent: greedy chain on the connectivity
+    normalised by the groups' volumes, W[a,b] / (vol_a * vol_b), with an exponentially decayed affinity to the
+    recently placed groups.  Host-side (numpy) over an S x S matrix, S <= 4096.  Returns (rank int64 [S], share of
+    the edges that stay inside a group)."""
+    import numpy as np
+    W = np.asarray(W, dtype=np.float64)
+    S = W.shape[0]
+    W = W + W.T                                     # symmetrise: in- and out-edges pull alike
+    tot = W.sum()
+    intra = float(np.trace(W) / tot) if tot > 0 else 0.0
+    vol = W.sum(1) + 1e-9
+    Wn = W / vol[:, None] / vol[None, :]
+    np.fill_diagonal(Wn, 0.0)
+    rank = np.zeros(S, dtype=np.int64)
+    aff = np.zeros(S)
+    cur = int(np.argmax(vol))
+    for pos in range(S):                            # in-place vector ops only: ~5 us per step
+        rank[cur] = pos
+        aff *= 0.5
+        aff += Wn[cur]
+        aff[cur] = -np.inf                          # placed groups can never win again (-inf survives decay and adds)
+        cur = int(aff.argmax())
+    return rank, intra
+
+
+def locality_groups(csr: "CSR", deg_order: torch.Tensor):
+    """(group int32 [N], n_groups) for the row schedule, or None when clustering is off / not worth it / finds no
+    community structure.  Seeded leaves-first label propagation on the device (rgbmp_cluster_lpa), group-to-group
+    connectivity on the device, chaining of the S groups on the host.  One small D2H (S*S*4 bytes) per graph."""
+    mode = CLUSTER
+    N, nnz = csr.n_rows, csr.nnz
+    if mode == "0" or csr.n_rows != csr.n_cols:
+        return None
+    if mode != "1" and (N < CLUSTER_MIN_NODES or nnz < CLUSTER_MIN_DEGREE * N):
+        return None
+    L = lib()
+    dev = csr.device
+    st = stream_of(dev)
+    S = int(min(CLUSTER_SEEDS, N))
+    plain = GraphStruct(csr.n_rows, csr.n_cols, csr.nnz, ptr(csr.rowptr), ptr(csr.col), 0, 0, 0, 0, None, None, None, None,
+                        None, 0)
+    import time
+    trace = os.environ.get("RGBMP_CLUSTER_TRACE")
+    if trace:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+    label = torch.empty(N, dtype=torch.int32, device=dev)
+    ws = _ws(L.rgbmp_cluster_workspace_bytes(N), dev)
+    taus = (C.c_float * len(CLUSTER_TAUS))(*CLUSTER_TAUS)
+    check(L.rgbmp_cluster_lpa(C.byref(plain), ptr(deg_order), S, len(CLUSTER_TAUS), taus, ptr(label), ptr(ws), ws.numel(),
+                              dev.index, st), "cluster_lpa")
+    if trace:
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+    W = torch.empty((S, S), dtype=torch.int32, device=dev)
+    check(L.rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, ptr(W), dev.index, st), "cluster_connectivity")
+    Wh = W.cpu().numpy().astype("int64") & 0xFFFFFFFF
+    if trace:
+        t2 = time.perf_counter()
+    rank, intra = chain_groups(Wh)
+    if trace:
+        print(f"[rgbmp cluster] lpa {1e3 * (t1 - t0):.2f} ms, connectivity + D2H {1e3 * (t2 - t1):.2f} ms, "
+              f"host chain {1e3 * (time.perf_counter() - t2):.2f} ms, intra {intra:.3f}", flush=True)
+    cluster_stats["built"] += 1
+    cluster_stats["last"] = {"groups": S, "intra_group_edge_share": round(intra, 4)}
+    if mode != "1" and intra < CLUSTER_MIN_INTRA:
+        return None
+    cluster_stats["used"] += 1
+    group = torch.from_numpy(rank).to(device=dev, dtype=torch.int32)[label.long()].contiguous()
+    return group, S
 
 
 class Graph:
@@ -195,7 +301,10 @@ class Graph:
             raise RuntimeError(f"edge_index contains node ids outside [0, {N})")
         self.nnz = nnz
         self.e_src, self.e_dst = e_src[:nnz], e_dst[:nnz]          # edited list: kept edges, then loops
-        self.fwd = CSR(self.e_dst, self.e_src, N, N, chunk, long_chunk, window)   # rows = targets i, col = sources j
+        self.fwd = CSR(self.e_dst, self.e_src, N, N, chunk, long_chunk, window, finish=False)   # rows = targets i, col = sources j
+        deg_order = self.fwd.degree_order() if (N > 1 and nnz > 0 and (window is None or window < 0)) else None
+        self.groups = locality_groups(self.fwd, deg_order) if deg_order is not None else None
+        self.fwd._finish(chunk, long_chunk, window, self.groups, deg_order)
         self._bwd: Optional[CSR] = None
         self._lock = threading.Lock()
         self._vals = {}
@@ -207,7 +316,8 @@ class Graph:
         if self._bwd is None:
             with self._lock:
                 if self._bwd is None:
-                    self._bwd = CSR(self.e_src, self.e_dst, self.N, self.N, self._chunk, self._long_chunk, self._window)
+                    self._bwd = CSR(self.e_src, self.e_dst, self.N, self.N, self._chunk, self._long_chunk, self._window,
+                                    groups=self.groups)     # the groups are a property of the NODES: same for both orientations
         return self._bwd
 
     def dinv(self) -> torch.Tensor:

@@ -16,6 +16,7 @@ from ._lib import Epilogue, check, dtype_code, lib, ptr, stream_of
 from .graph import CSR, Graph, NORM_COUNT, NORM_INV_SQRT, oom_retry
 
 RESET_NONE, RESET_BEFORE_TELEPORT, RESET_AFTER_CLAMP = 0, 1, 2
+TUNE_OVERRIDE = 0      # experiments (tools/): launch-shape word applied to every SpMM / K-hop call that passes tune=0
 
 
 # ------------------------------------------------------------------------------------------
@@ -95,6 +96,7 @@ def _spmm_raw(csr: CSR, x: torch.Tensor, val: Optional[torch.Tensor] = None, *, 
               store_local: bool = True) -> Optional[torch.Tensor]:
     """`keep` holds tensors referenced by `ep`.
     hot=True lets feature matrices beyond the L2 budget use the hot-tagged column ids (graph.CSR.hot_ref)."""
+    tune = tune or TUNE_OVERRIDE
     xb, ldx = as_rows(x)
     F = x.size(1)
     if x.size(0) < csr.n_cols:
@@ -129,6 +131,7 @@ def khop_raw(csr: CSR, x0: torch.Tensor, K: int, **kw):
 
 def _khop_raw(csr: CSR, x0: torch.Tensor, K: int, *, val=None, ep: Optional[Epilogue] = None, keep=(),
               hops: bool = False, tune: int = 0, hot: bool = True):
+    tune = tune or TUNE_OVERRIDE
     xb, ldx = as_rows(x0)
     N, F = x0.shape
     dev, dt = x0.device, x0.dtype

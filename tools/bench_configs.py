@@ -36,7 +36,7 @@ def out(**kw):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="build,c1,c2,c3,c4")
+    ap.add_argument("--only", default="build,c1,c2,c3,att,c4")
     args = ap.parse_args()
     only = set(args.only.split(","))
     import rgb_experiment_b200 as P
@@ -198,6 +198,68 @@ def main():
             peak_mem_GiB=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
             note="1 train fwd+bwd+Adam + 2 eval fwd; PyG materialises [nnz,8,8] = 29.4 GB per layer-forward here (SURVEY 8a a4)")
         del sgx, g, m
+
+    if "att" in only:
+        # the two layers that were an unfused chain in round 1: SuperGATConv-MX 8x8 on the arxiv-shaped graph (the
+        # reference's OOM cell, 最终结果.csv:69) and on the Reddit-shaped one, FAConv F=64 on arxiv / products shapes
+        for wl, mode in (("arxiv", P.LOOP_REMOVE_THEN_ADD), ("reddit", P.LOOP_REMOVE_THEN_ADD)):
+            sg = S.make_named(wl, device=dev, features=False)
+            N = sg.num_nodes
+            g = P.Graph(sg.edge_index, N, mode)
+            _ = g.bwd
+            H, C = 8, 8
+            xp = (torch.randn(N, H * C, device=dev) * 0.3).requires_grad_(True)
+            a_l = torch.randn(N, H, device=dev, requires_grad=True)
+            a_r = torch.randn(N, H, device=dev, requires_grad=True)
+            do = torch.randn(N, H * C, device=dev)
+            P.memo.set_budget_mb(0)
+            torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.memory_allocated()
+            with torch.no_grad():
+                fwd = ev_ms(lambda: P.ops.supergat_mx(xp.detach(), a_l.detach(), a_r.detach(), g, H, C, 0.2), 5, 2)
+            peak_eval = torch.cuda.max_memory_allocated() - base
+
+            def fb():
+                o = P.ops.supergat_mx(xp, a_l, a_r, g, H, C, 0.2)
+                o.backward(do)
+                xp.grad = a_l.grad = a_r.grad = None
+
+            fbm = ev_ms(fb, 3, 1)
+            # algorithmic bytes (gather model): forward gathers X[j] (H*C*4) + a_l[j] (H*4) + col per edge; the MX backward
+            # gathers dout_i + x_i + stats per edge on the transpose and x_j + a_l on the forward CSR
+            Bf = g.nnz * (H * C * 4 + H * 4 + 4) + 2 * N * H * C * 4 + 3 * N * H * 4
+            out(config=f"SuperGATConv-MX H={H} C={C} fused, {wl}-shaped", nnz=g.nnz, fwd_ms=fwd, fwd_gteps=g.nnz / fwd / 1e6,
+                fwd_GBps=Bf / fwd / 1e6, frac_of_measured_hbm=Bf / fwd / 1e6 / PEAK, fwd_bwd_ms=fbm,
+                eval_forward_extra_bytes=peak_eval, one_nnzH_tensor_bytes=g.nnz * H * 4)
+            P.memo.set_budget_mb(4096)
+            del sg, g, xp, a_l, a_r, do
+        for wl in ("arxiv", "products"):
+            sg = S.make_named(wl, device=dev, features=False)
+            N = sg.num_nodes
+            g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
+            _ = g.bwd
+            Fh = 64
+            x = torch.randn(N, Fh, device=dev, requires_grad=True)
+            a_l = torch.randn(N, 1, device=dev, requires_grad=True)
+            a_r = torch.randn(N, 1, device=dev, requires_grad=True)
+            do = torch.randn(N, Fh, device=dev)
+            P.memo.set_budget_mb(0)
+            with torch.no_grad():
+                fwd = ev_ms(lambda: P.ops.faconv(x.detach(), a_l.detach(), a_r.detach(), g), 5, 2)
+
+            def fb2():
+                o = P.ops.faconv(x, a_l, a_r, g)
+                o.backward(do)
+                x.grad = a_l.grad = a_r.grad = None
+
+            fbm = ev_ms(fb2, 3, 1)
+            Bf = g.nnz * (Fh * 4 + 4 + 4 + 4) + 2 * N * Fh * 4 + (N + 1) * 8
+            spmm = ev_ms(lambda: P.ops.propagate(x.detach(), g, "gcn"), 5, 2)
+            out(config=f"FAConv F={Fh} fused, {wl}-shaped", nnz=g.nnz, fwd_ms=fwd, fwd_gteps=g.nnz / fwd / 1e6,
+                fwd_GBps=Bf / fwd / 1e6, frac_of_measured_hbm=Bf / fwd / 1e6 / PEAK, fwd_bwd_ms=fbm,
+                plain_gcn_spmm_same_shape_ms=spmm)
+            P.memo.set_budget_mb(4096)
+            del sg, g, x, a_l, a_r, do
 
     if "c4" in only:
         sg = S.make_named("products", device=dev, features=False)

@@ -40,34 +40,36 @@ def time_ms(fn, iters=3):
     return e0.elapsed_time(e1) / iters
 
 
-def lpa_labels(rowptr, col, n, seeds, iters):
-    """Seeded synchronous label propagation: the S highest-degree nodes keep their own label; every other node
-    takes the most frequent label among its labelled in-neighbours (ties: smallest label)."""
+def lpa_labels(rowptr, col, n, seeds, iters, taus=(0.3, 0.15, 0.05, 0.0, 0.0, 0.0)):
+    """Seeded label propagation, leaves first: the S highest-degree nodes keep their own label; in round t an
+    UNLABELLED node takes the most frequent label among its labelled in-neighbours (ties: smallest label) once at
+    least taus[t] of its neighbours carry one, and keeps it.  The threshold makes hubs wait for their own leaves
+    instead of copying a bigger hub across one of the (few, but heavy) hub-hub edges."""
     dev = rowptr.device
     deg = rowptr[1:] - rowptr[:-1]
     order = torch.argsort(deg, descending=True, stable=True)
     S = seeds
     label = torch.full((n,), -1, dtype=torch.int64, device=dev)
     label[order[:S]] = torch.arange(S, device=dev)
-    is_seed = torch.zeros(n, dtype=torch.bool, device=dev)
-    is_seed[order[:S]] = True
     row = torch.repeat_interleave(torch.arange(n, device=dev), deg)
     colL = col.long()
     for it in range(iters):
+        tau = taus[min(it, len(taus) - 1)]
         lj = label[colL]
         m = lj >= 0
+        nlab = torch.zeros(n, dtype=torch.int64, device=dev).index_add_(0, row[m], torch.ones_like(row[m]))
         key = row[m] * S + lj[m]
         uk, cnt = torch.unique(key, return_counts=True)
         r, l = uk // S, uk % S
         score = cnt * S + (S - 1 - l)
         best = torch.full((n,), -1, dtype=torch.int64, device=dev)
         best.scatter_reduce_(0, r, score, reduce="amax", include_self=True)
-        new = torch.where(best >= 0, S - 1 - (best % S), label)
-        new = torch.where(is_seed, label, new)
+        ok = (label < 0) & (best >= 0) & (nlab.double() >= tau * deg.double())
+        new = torch.where(ok, S - 1 - (best % S), label)
         changed = int((new != label).sum())
         label = new
-        print(json.dumps({"lpa_iter": it, "changed": changed, "unlabelled": int((label < 0).sum())}), flush=True)
-        del lj, m, key, uk, cnt, r, l, score, best
+        print(json.dumps({"lpa_iter": it, "tau": tau, "changed": changed, "unlabelled": int((label < 0).sum())}), flush=True)
+        del lj, m, key, uk, cnt, r, l, score, best, nlab
     label = torch.where(label < 0, torch.zeros_like(label), label)
     return label, row
 
@@ -128,10 +130,11 @@ def main():
     ap.add_argument("--workload", default="products")
     ap.add_argument("--F", type=int, default=47)
     ap.add_argument("--seeds", default="1024")
-    ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--variants", default="base,lpa,oracle")
     ap.add_argument("--policies", default="default,off")
     ap.add_argument("--hops", type=int, default=10)
+    ap.add_argument("--tunes", default="0", help="comma list of G:V:U launch shapes (0 = the library default)")
     args = ap.parse_args()
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.synth as S
@@ -143,15 +146,21 @@ def main():
     z0p, _ = P.ops.as_rows(z0)
 
     def bench(g, tag, extra):
-        for pol in args.policies.split(","):
-            hot_saved = G_.HOT_L2_BYTES
-            if pol == "off":
-                G_.HOT_L2_BYTES = 0
-            g.fwd._tagged = {}
-            ms = time_ms(lambda: P.ops._appnp_khop(g.fwd, g, z0p, args.hops, 0.1, False, True)) / args.hops
-            G_.HOT_L2_BYTES = hot_saved
-            print(json.dumps({"variant": tag, "policy": pol, "ms_per_hop": round(ms, 4),
-                              "gteps": round(g.nnz / ms / 1e6, 2), **extra}), flush=True)
+        for tn in args.tunes.split(","):
+            P.ops.TUNE_OVERRIDE = 0
+            if tn != "0":
+                G__, V__, U__ = (int(v) for v in tn.split(":"))
+                P.ops.TUNE_OVERRIDE = G__ | (V__ << 8) | (U__ << 16)
+            for pol in args.policies.split(","):
+                hot_saved = G_.HOT_L2_BYTES
+                if pol == "off":
+                    G_.HOT_L2_BYTES = 0
+                g.fwd._tagged = {}
+                ms = time_ms(lambda: P.ops._appnp_khop(g.fwd, g, z0p, args.hops, 0.1, False, True)) / args.hops
+                G_.HOT_L2_BYTES = hot_saved
+                print(json.dumps({"variant": tag, "policy": pol, "tune": tn, "ms_per_hop": round(ms, 4),
+                                  "gteps": round(g.nnz / ms / 1e6, 2), **extra}), flush=True)
+        P.ops.TUNE_OVERRIDE = 0
 
     variants = args.variants.split(",")
     g = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
