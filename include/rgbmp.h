@@ -350,6 +350,16 @@ int rgbmp_spmm_heads(const rgbmp_graph_t* g, const float* w, const float* X, int
                      int H, int C, float* out, int64_t ldo, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (c2) measurement aid: random ROW-GATHER peak of the device (csrc/microbench.cu).  n_groups groups of
+ * row_bytes/16 lanes each read `gathers_per_group` random rows of `table` [n_rows, row_bytes] with 16-byte loads
+ * (8 rows in flight per lane, ids from a counter hash) and write one 16-byte checksum per group to `out`.
+ * Bytes gathered = n_groups * gathers_per_group * row_bytes; timed by the caller.  The roofline denominator of
+ * aggregation kernels whose feature matrix is L2-resident (bench.py --workload arxiv_sage / reddit_gat).
+ * ------------------------------------------------------------------------------------------ */
+int rgbmp_microbench_gather(const void* table, int64_t n_rows, int row_bytes, int64_t gathers_per_group,
+                            uint32_t seed, void* out, int64_t n_groups, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (d) host-buffer entry point (end-to-end form of the hot path: H2D -> K hops -> D2H)
  * ------------------------------------------------------------------------------------------ */
 

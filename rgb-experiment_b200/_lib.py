@@ -95,6 +95,7 @@ def lib():
         "rgbmp_l2_persist": (C.c_int, [C.c_int, c_sz, c_vp]),
         "rgbmp_col_freq": (C.c_int, [c_vp, c_i64, c_i64, c_vp, C.c_int, c_vp]),
         "rgbmp_col_tag": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_vp, C.c_int, c_vp]),
+        "rgbmp_microbench_gather": (C.c_int, [c_vp, c_i64, C.c_int, c_i64, C.c_uint32, c_vp, c_i64, C.c_int, c_vp]),
         "rgbmp_rowdot": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
         "rgbmp_sddmm": (C.c_int, [GP, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
         "rgbmp_u_add_v": (C.c_int, [GP, c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp]),

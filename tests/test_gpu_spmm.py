@@ -95,7 +95,7 @@ def test_every_launch_shape_gives_the_same_answer():
     outs = []
     for G in (1, 2, 4, 8, 16, 32):
         for V in (1, 2):
-            for U in (2, 4, 18, 20):
+            for U in (2, 4, 8, 18, 20):
                 y = p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=G | (V << 8) | (U << 16))
                 assert relerr(y, ref) <= TOL, (G, V, U)
                 outs.append(y)
@@ -105,7 +105,7 @@ def test_every_launch_shape_gives_the_same_answer():
     for y in outs[1:]:
         assert torch.equal(y[short], outs[0][short])
     # shapes that are no longer instantiated are rejected, not silently replaced
-    for bad in (1 | (3 << 8) | (4 << 16), 8 | (1 << 8) | (8 << 16), 3 | (1 << 8) | (4 << 16)):
+    for bad in (1 | (3 << 8) | (4 << 16), 8 | (1 << 8) | (16 << 16), 3 | (1 << 8) | (4 << 16)):
         with pytest.raises(RuntimeError):
             p.ops.spmm_raw(g.fwd, xd, g.gcn_val(False), tune=bad)
 
