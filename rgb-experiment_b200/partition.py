@@ -53,6 +53,15 @@ class Grid:
                 if r == self.rp:
                     self.col_group = g
 
+    def warm_up(self, device) -> None:
+        """One tiny collective on every group this rank belongs to: NCCL builds a sub-communicator lazily, at the
+        first collective (seconds on an 8-GPU box) -- pay it here, not inside a timed graph build or step."""
+        t = torch.zeros(1, device=device)
+        for g in (None, self.row_group, self.col_group):
+            if g is not None or self.world > 1:
+                dist.all_reduce(t, group=g)
+        torch.cuda.synchronize(device)
+
     def feature_slice(self, F: int, align: int = 4, fp: Optional[int] = None):
         """[lo, hi) of the feature columns of feature group `fp` (default: mine).  Slices start on
         `align`-element boundaries (16-byte vectors) and the vector units are spread evenly."""
@@ -150,12 +159,28 @@ class LocalBlock:
         self.N, self.rank, self.world = N, rank, world
         self.R = rows_per_rank(N, world)
         self.lo, self.hi = row_range(N, rank, world)
+        # locality groups of the row schedule (graph.locality_groups): a property of the NODES of the whole graph, so
+        # every rank derives them from the (replicated) edge list and gets the same answer without communication;
+        # the transposed block reuses the forward block's
+        from .graph import locality_groups
+        if transpose_of is not None:
+            self.groups = transpose_of.groups
+        else:
+            whole = CSR(e_dst[:nnz], e_src[:nnz], N, N, finish=False)
+            self.groups = locality_groups(whole, whole.degree_order()) if N > 1 and nnz > 0 else None
+            del whole
         if transpose_of is None:
             key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
         else:                                   # bucket by SOURCE: row = local source id, col = global target id
             key, other = local_edges(e_dst[:nnz], e_src[:nnz], self.lo, self.hi)
         del e_src, e_dst
-        self.csr = CSR(key, other, self.R, self.R * world)
+        local_groups = None
+        if self.groups is not None:
+            grp, n_groups = self.groups
+            mine = torch.zeros(self.R, dtype=torch.int32, device=dev)
+            mine[: self.hi - self.lo] = grp[self.lo:self.hi]
+            local_groups = (mine, n_groups)
+        self.csr = CSR(key, other, self.R, self.R * world, groups=local_groups)
         self._norms(group, transpose_of)
 
     @classmethod
@@ -168,6 +193,7 @@ class LocalBlock:
         self.N, self.rank, self.world = n_nodes, rank, world
         self.R = rows_per_rank(n_nodes, world)
         self.lo, self.hi = row_range(n_nodes, rank, world)
+        self.groups = None
         rowptr, col = synth.rowgen_block(n_nodes, n_edges, self.lo, self.hi, device=device, **gen_kw)
         if self.hi - self.lo < self.R:             # pad the last block with empty rows
             rowptr = torch.cat([rowptr, rowptr[-1:].expand(self.R - (self.hi - self.lo))])

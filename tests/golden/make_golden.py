@@ -10,10 +10,11 @@ Reference code executed verbatim (imported from /root/reference, never copied):
   * rgb_experiment/itexperiments.py:698-719  label_propagation
   * rgb_experiment/models/pta.py:79-84       PTA.inference
   * rgb_experiment/models/dagnn.py:12-31     gcn_norm  (its two helpers, add_remaining_self_loops
-                                             and scatter_add, come from the oracle shim -- they
-                                             are PyG/torch_scatter functions absent here)
-  * rgb_experiment/models/dagnn.py:34-65     Prop.forward / message (MessagePassing base from the shim)
-  * rgb_experiment/models/graphsage.py:36-62 my_SAGEConv.forward (MessagePassing base from the shim)
+                                             and scatter_add -- PyG/torch_scatter functions absent
+                                             here -- come from tests/golden/independent_stubs.py:
+                                             plain Python loops that share NO code with oracle/)
+  * rgb_experiment/models/dagnn.py:34-65     Prop.forward / message (loop MessagePassing base from the stubs)
+  * rgb_experiment/models/graphsage.py:36-62 my_SAGEConv.forward (loop MessagePassing base from the stubs)
   * rgb_experiment/utils/mask.py:10-21       get_whole_mask (decides the split)
 
 Outputs: tests/golden/*.npz (small; committed).
@@ -28,7 +29,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from oracle import shim  # noqa: E402
+from oracle import shim  # noqa: E402  (only its matplotlib stub is used)
+sys.path.insert(0, HERE)
+import independent_stubs  # noqa: E402
 
 
 def small_graph(seed, n, e, self_loops=0, dups=0):
@@ -49,7 +52,8 @@ def small_graph(seed, n, e, self_loops=0, dups=0):
 
 
 def main():
-    shim.install()
+    shim.install_matplotlib_stub()
+    independent_stubs.install()
     sys.path.insert(0, "/root/reference")
     import scipy.sparse as sp
     from rgb_experiment import itexperiments as IT

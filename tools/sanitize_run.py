@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""The small-graph workout run under compute-sanitizer (SURVEY.md section 5 "race detection"):
+every kernel family of librgbmp.so on the edge-case graphs of tests/helpers.CASES -- graph build (all three radix
+variants), loop edits, coalesce, locality groups, SpMM (vector, scalar / unaligned, bf16, long rows, every epilogue),
+K-hop, fused attention forward + backward for GAT / SuperGAT-MX / FAConv (all head shape classes, long rows), the
+generic edge-score kernels.  One tool per call:
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_run.py
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+    compute-sanitizer --tool initcheck python tools/sanitize_run.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import rgb_experiment_b200 as P
+    from rgb_experiment_b200 import graph as G
+    import rgb_experiment_b200.shim.utils as U
+    from helpers import CASES
+    dev = torch.device("cuda:0")
+    G.CLUSTER_SEEDS = 16
+    n_calls = 0
+    for variant in ("3", "1", "2"):
+        os.environ["RGBMP_BUILD_VARIANT"] = variant
+        for name in ("tiny", "loops_dups", "isolated", "hub", "empty", "single_node"):
+            ei, n = CASES[name]()
+            for mode in (P.LOOP_NONE, P.LOOP_ADD, P.LOOP_ADD_REMAINING, P.LOOP_REMOVE_THEN_ADD):
+                g = P.Graph(ei.to(dev), n, mode)
+                _ = g.bwd
+                n_calls += 1
+    os.environ["RGBMP_BUILD_VARIANT"] = "3"
+    for name in ("loops_dups", "isolated", "hub"):
+        ei, n = CASES[name]()
+        eid = ei.to(dev)
+        U.to_undirected(eid, n)
+        U.coalesce(eid, None, n, n)
+        G.CLUSTER = "1"
+        g = P.Graph(eid, n, P.LOOP_ADD_REMAINING)              # locality groups forced on: LPA + connectivity + grouped order
+        G.CLUSTER = "auto"
+        gn = P.Graph(eid, n, P.LOOP_NONE)
+        gr = P.Graph(eid, n, P.LOOP_REMOVE_THEN_ADD)
+        gen = torch.Generator(device=dev).manual_seed(0)
+        for F, dt in ((48, torch.float32), (23, torch.float32), (7, torch.float32), (100, torch.float32), (260, torch.float32),
+                      (64, torch.bfloat16)):
+            x = torch.randn(n, F, device=dev, generator=gen).to(dt)
+            if dt == torch.float32:
+                x.requires_grad_(True)
+                for kind in ("sum", "mean", "gcn"):
+                    P.ops.propagate(x, g, kind).sum().backward()
+                P.ops.appnp(x, g, 3, 0.1, False).sum().backward()
+                P.ops.appnp(x, g, 3, 0.1, True).sum().backward()
+                P.ops.gcn_power(x.detach(), g, 2)
+                m = torch.zeros(n, dtype=torch.bool, device=dev)
+                m[::3] = True
+                P.ops.label_propagation(gn, x.detach(), 3, 0.8, clamp=(-1.0, 1.0))
+                P.ops.label_propagation(gn, x.detach(), 3, 0.8, reset_mask=m, reset_val=x.detach())
+                w = torch.rand(g.nnz, device=dev, generator=gen, requires_grad=True)
+                P.ops.propagate_weighted(x, w, g).sum().backward()
+            else:
+                P.ops.spmm_raw(g.fwd, x, None)
+            n_calls += 8
+        for H, C in ((8, 8), (1, 41), (3, 5), (5, 32), (2, 47)):
+            xp = (torch.randn(n, H * C, device=dev, generator=gen) * 0.5).requires_grad_(True)
+            a = torch.randn(n, H, device=dev, generator=gen, requires_grad=True)
+            b = torch.randn(n, H, device=dev, generator=gen, requires_grad=True)
+            keep = (torch.rand(gr.nnz, H, device=dev, generator=gen) > 0.3).float() / 0.7
+            for drop in (None, keep):
+                P.ops.gat(xp, a, b, gr, H, C, 0.2, drop).sum().backward()
+                P.ops.supergat_mx(xp, a, b, gr, H, C, 0.2, drop).sum().backward()
+            with torch.no_grad():
+                P.ops.gat(xp, a, b, gr, H, C, 0.2)
+                P.ops.supergat_mx(xp, a, b, gr, H, C, 0.2)
+            n_calls += 6
+        for C in (64, 7):
+            x = torch.randn(n, C, device=dev, generator=gen, requires_grad=True)
+            al = torch.randn(n, 1, device=dev, generator=gen, requires_grad=True)
+            ar = torch.randn(n, 1, device=dev, generator=gen, requires_grad=True)
+            P.ops.faconv(x, al, ar, g).sum().backward()
+            P.ops.faconv(x, al, ar, g, (torch.rand(g.nnz, device=dev, generator=gen) > 0.5).float() * 2).sum().backward()
+        A = torch.randn(n, 18, device=dev, generator=gen, requires_grad=True)
+        s = P.ops.edge_sddmm(A, A, gn, 3, 6)
+        P.ops.spmm_heads(P.ops.edge_softmax(s, gn), A, gn, 3, 6).sum().backward()
+        u = torch.randn(n, 3, device=dev, generator=gen, requires_grad=True)
+        P.ops.edge_u_add_v(u, u, gn).sum().backward()
+    torch.cuda.synchronize()
+    print(f"sanitize_run ok: {n_calls} op groups")
+
+
+if __name__ == "__main__":
+    main()
