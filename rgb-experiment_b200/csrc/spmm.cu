@@ -1,4 +1,5 @@
 // CSR SpMM host-side dispatch, K-hop driver, host-buffer entry point (sm_100a).
+#include <stdlib.h>
 #include <string.h>
 #include "spmm_kernels.cuh"
 
@@ -62,9 +63,14 @@ static int check_graph(const rgbmp_graph_t* g, const char* fn) {
   return 0;
 }
 
-static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,
-                     int dtype, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, cudaStream_t st) {
+struct Prepared {
   SpmmParams p;
+  int G, V, U, epv;
+};
+
+static int spmm_prepare(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,
+                        int dtype, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, Prepared* out) {
+  SpmmParams& p = out->p;
   p.rowptr = g->rowptr;
   p.col = g->col;
   p.val = val;
@@ -144,9 +150,21 @@ static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, in
     if (!pow2 || V < 1 || V > 2 || (U != 2 && U != 4 && U != 8 && U != 18 && U != 20))
       return fail(RGBMP_EINVAL, "rgbmp_spmm: bad tune word 0x%x", tune);
   }
-  if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(p, G, V, U, st);
-  if (epv == 4) return spmm_dispatch_f32v(p, G, V, U, st);
-  return spmm_dispatch_f32s(p, G, V, U, st);
+  out->G = G;
+  out->V = V;
+  out->U = U;
+  out->epv = epv;
+  return 0;
+}
+
+static int spmm_impl(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,
+                     int dtype, const rgbmp_epilogue_t* ep, int tune, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Prepared pr;
+  const int rc = spmm_prepare(g, val, X, ldx, Y, ldy, F, dtype, ep, tune, ws, ws_bytes, &pr);
+  if (rc) return rc;
+  if (dtype == RGBMP_BF16) return spmm_dispatch_bf16(pr.p, pr.G, pr.V, pr.U, st);
+  if (pr.epv == 4) return spmm_dispatch_f32v(pr.p, pr.G, pr.V, pr.U, st);
+  return spmm_dispatch_f32s(pr.p, pr.G, pr.V, pr.U, st);
 }
 
 }  // namespace rgbmp

@@ -25,6 +25,16 @@ NORM_INV_SQRT, NORM_INV_MEAN, NORM_COUNT = 0, 1, 2
 
 DEFAULT_CHUNK = 1024        # rows with more edges than this are split ...
 DEFAULT_LONG_CHUNK = 4096   # ... into CTA work items of this many edges
+# Small graphs (fewer rows than one wave of row groups keeps busy): a hop is a few microseconds of work and its
+# latency is the LONGEST row's chain of dependent gathers (~0.4 us per 8-edge step: the Cora-shaped hub of 251 edges
+# alone takes 25 of the hop's 31 us), not launch overhead -- so rows are split much earlier.  Measured, Cora-shaped
+# APPNP K=10 F=7: 307 us with chunk 1024, 184 us with 64/512, 162 us with 32/256 (profiles/r02_small_graph_latency.txt).
+SMALL_GRAPH_ROWS = 148 * 4 * 32
+SMALL_CHUNK, SMALL_LONG_CHUNK = 32, 256
+
+
+def default_chunks(n_rows: int):
+    return (SMALL_CHUNK, SMALL_LONG_CHUNK) if n_rows < SMALL_GRAPH_ROWS else (DEFAULT_CHUNK, DEFAULT_LONG_CHUNK)
 HOT_L2_BYTES = 64 << 20     # L2 budget for the hot (most gathered) feature rows; 0 turns the tagging off
 DEFAULT_WINDOW = -1         # row schedule: -1 = global degree sort (fastest on B200, profiles/r01_sweep_v2.txt),
                             # w > 0 = degree-sorted inside windows of w rows, 0 = natural order
@@ -49,7 +59,7 @@ class CSR:
     (position in the edited edge list), plus the long-row work lists and the ctypes descriptor."""
 
     def __init__(self, key: torch.Tensor, other: torch.Tensor, n_rows: int, n_cols: int,
-                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None,
+                 chunk: Optional[int] = None, long_chunk: Optional[int] = None, window: Optional[int] = None,
                  groups=None, finish: bool = True):
         L = lib()
         dev = key.device
@@ -68,8 +78,8 @@ class CSR:
             self._finish(chunk, long_chunk, window, groups)
 
     @classmethod
-    def from_arrays(cls, rowptr: torch.Tensor, col: torch.Tensor, n_cols: int, chunk: int = DEFAULT_CHUNK,
-                    long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None) -> "CSR":
+    def from_arrays(cls, rowptr: torch.Tensor, col: torch.Tensor, n_cols: int, chunk: Optional[int] = None,
+                    long_chunk: Optional[int] = None, window: Optional[int] = None) -> "CSR":
         """Wrap a CSR that exists already (row-generated graphs, synth.rowgen_block): rowptr int64
         [n_rows+1], col int32 [nnz] on the device.  No edge ids (eid is None)."""
         _lib.require_cuda(rowptr, "rowptr")
@@ -98,7 +108,8 @@ class CSR:
         L = lib()
         dev, n_rows, nnz = self.device, self.n_rows, self.nnz
         st = stream_of(dev)
-        self.chunk, self.long_chunk = int(chunk), int(long_chunk)
+        dc, dl = default_chunks(n_rows)
+        self.chunk, self.long_chunk = int(dc if chunk is None else chunk), int(dl if long_chunk is None else long_chunk)
         self.n_long = self.n_items = 0
         self.long_rows = self.long_item_ptr = self.item_long = self.item_start = None
         self.row_order = None
@@ -279,7 +290,7 @@ class Graph:
     """Edited edge list + forward CSR (+ lazy transpose CSR, normalisation vectors, edge weights)."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int, loop_mode: int = LOOP_NONE,
-                 chunk: int = DEFAULT_CHUNK, long_chunk: int = DEFAULT_LONG_CHUNK, window: Optional[int] = None):
+                 chunk: Optional[int] = None, long_chunk: Optional[int] = None, window: Optional[int] = None):
         _lib.require_cuda(edge_index, "edge_index")
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise RuntimeError("edge_index must be an int64 tensor of shape [2, E]")

@@ -53,10 +53,16 @@ def as_rows(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
 
 
 def alloc_rows(N: int, F: int, dtype, device) -> Tuple[torch.Tensor, int]:
-    """[N, F] view of a fresh [N, padded(F)] buffer."""
+    """Fresh [N, F] tensor whose rows are padded(F) elements apart (16-byte aligned rows for the vector kernels).
+    NOT a view: the result of an autograd.Function must tolerate the caller's in-place update (`out += x_r`,
+    graphsage.py:60), which autograd forbids on a view created inside a custom Function -- so the
+    strided tensor is bound to the padded storage directly instead of slicing a [N, padded(F)] tensor."""
     Fp = padded_width(F, dtype)
     buf = torch.empty((N, Fp), dtype=dtype, device=device)
-    return (buf if Fp == F else buf[:, :F]), Fp
+    if Fp == F:
+        return buf, Fp
+    out = torch.empty(0, dtype=dtype, device=device).set_(buf.untyped_storage(), 0, (N, F), (Fp, 1))
+    return out, Fp
 
 
 def make_epilogue(*, row_scale=None, row_div=False, a=1.0, b=0.0, T=None, ldt=0, clamp=None,

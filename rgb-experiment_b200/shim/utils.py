@@ -122,7 +122,13 @@ def add_remaining_self_loops(edge_index, edge_weight=None, fill_value=1.0, num_n
         inv = ~mask
         rem = edge_weight[inv]
         if rem.numel() > 0:
-            lw[row[inv]] = rem
+            # an existing loop keeps its weight, the LAST one when a node has several (A3; PyG's CPU index_put order).
+            # An index_put with duplicate indices is unordered on CUDA, so the last occurrence is selected explicitly.
+            nodes = row[inv]
+            pos = torch.arange(nodes.numel(), device=nodes.device)
+            last = torch.full((N,), -1, dtype=torch.long, device=nodes.device).scatter_reduce_(0, nodes, pos, reduce="amax")
+            has = last >= 0
+            lw[has] = rem[last[has]]
         edge_weight = torch.cat([edge_weight[mask], lw])
     return out, edge_weight
 

@@ -160,3 +160,4 @@ def test_host_buffer_entry_point_matches_device_path():
     p.ops.appnp_host(g, z0, out, K, alpha)
     ref = R.appnp_propagate(z0.double(), ei, K, alpha)
     assert relerr(out, ref) <= TOL
+

@@ -97,8 +97,9 @@ def test_in_place_add_on_propagate_output_is_legal(ref):
     import rgb_experiment.models.graphsage as SG
     x, y, ei = cache.get("mid") or EC.make_data("mid")
     dev = "cuda:0"
-    conv = SG.my_SAGEConv(x.size(1), 16).to(dev)
-    xd = x.to(dev).requires_grad_(True)
-    out = conv(xd, ei.to(dev))
-    out.sum().backward()
-    assert torch.isfinite(xd.grad).all() and xd.grad.abs().sum() > 0
+    for width in (16, 10):                 # 10: rows padded to 12 floats -- the propagate result must still not be a view
+        conv = SG.my_SAGEConv(x.size(1), width).to(dev)
+        xd = x.to(dev).requires_grad_(True)
+        out = conv(xd, ei.to(dev))
+        out.sum().backward()
+        assert torch.isfinite(xd.grad).all() and xd.grad.abs().sum() > 0
