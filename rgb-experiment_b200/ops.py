@@ -61,7 +61,7 @@ def alloc_rows(N: int, F: int, dtype, device) -> Tuple[torch.Tensor, int]:
     buf = torch.empty((N, Fp), dtype=dtype, device=device)
     if Fp == F:
         return buf, Fp
-    out = torch.empty(0, dtype=dtype, device=device).set_(buf.untyped_storage(), 0, (N, F), (Fp, 1))
+    out = torch.empty(0, dtype=dtype, device=device).set_(buf.untyped_storage(), buf.storage_offset(), (N, F), (Fp, 1))
     return out, Fp
 
 
@@ -293,10 +293,30 @@ def gcn_power(x, graph: Graph, K: int, fold: Optional[bool] = None):
                        lambda: _PowerHops.apply(x, graph, int(K), fold))
 
 
+class _DagnnHops(torch.autograd.Function):
+    """[N, K+1, C] stack (x, A_hat x, ..., A_hat^K x) in one K-hop call that keeps every hop (dagnn.py:43-49).
+    Backward: g_K = dS_K; g_k = dS_k + A_hat^T g_{k+1} -- K transposed SpMMs with the add in the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, graph: Graph, K: int):
+        ctx.graph, ctx.K = graph, K
+        _, hops = khop_raw(graph.fwd, x, K, val=graph.gcn_val(False), hops=True)
+        return torch.cat([x.detach().unsqueeze(0), hops], dim=0).permute(1, 0, 2)
+
+    @staticmethod
+    def backward(ctx, dS):
+        g, K = ctx.graph, ctx.K
+        val = g.gcn_val(True)
+        acc = dS[:, K, :].contiguous()
+        for k in range(K - 1, -1, -1):
+            t, ldt = as_rows(dS[:, k, :])
+            acc = spmm_raw(g.bwd, acc, val, ep=make_epilogue(a=1.0, b=1.0, T=t, ldt=ldt), keep=(t,))
+        return acc, None, None
+
+
 def dagnn_hops(x: torch.Tensor, graph: Graph, K: int) -> torch.Tensor:
-    """[N, K+1, C] stack of x and its K propagated versions (dagnn.py:43-49), forward only."""
-    _, hops = khop_raw(graph.fwd, x, K, val=graph.gcn_val(False), hops=True)
-    return torch.cat([x.unsqueeze(0), hops], dim=0).permute(1, 0, 2)
+    """[N, K+1, C] stack of x and its K propagated versions (dagnn.py:43-49), differentiable."""
+    return _DagnnHops.apply(x, graph, int(K))
 
 
 def label_propagation(graph: Graph, out0: torch.Tensor, num_layers: int, alpha: float, *,

@@ -161,3 +161,20 @@ def test_host_buffer_entry_point_matches_device_path():
     ref = R.appnp_propagate(z0.double(), ei, K, alpha)
     assert relerr(out, ref) <= TOL
 
+
+
+@pytest.mark.parametrize("case", ["loops_dups", "hub"])
+def test_dagnn_hops_backward(case):
+    """ops.dagnn_hops keeps every hop in one K-hop call and is differentiable (backward = K transposed SpMMs)."""
+    p = P()
+    ei, n = CASES[case]()
+    g = p.Graph(ei.to(DEV), n, p.LOOP_ADD_REMAINING)
+    x = torch.randn(n, 5, generator=torch.Generator().manual_seed(2))
+    dS = torch.randn(n, 4, 5, generator=torch.Generator().manual_seed(3))
+    xo = x.double().requires_grad_(True)
+    R.dagnn_hops(xo, ei, 3).backward(dS.double())
+    xg = x.to(DEV).requires_grad_(True)
+    out = p.ops.dagnn_hops(xg, g, 3)
+    out.backward(dS.to(DEV))
+    assert relerr(out.detach(), R.dagnn_hops(x.double(), ei, 3)) <= TOL
+    assert relerr(xg.grad, xo.grad) <= TOL
