@@ -42,11 +42,13 @@ pack_rows_kernel(const float* __restrict__ X, int64_t ld, float* __restrict__ Y,
 //     U4 0.307 vs 0.459); rows wider than 64 vectors are tiled over blockIdx.y;
 //   * narrow rows: 8 lanes x 8 edges for 5-8 vectors (F=24/32: 1.81 / 1.74 ms), 4 lanes below that -- pipelined
 //     for 1-2 vectors, where two idle lanes still beat the 2-lane group (F=8: 0.86 vs 1.08 ms).
+//   * when the gathers come from HBM (feature matrix well beyond L2) 4 edges in flight at 5 CTAs per SM (40 registers)
+//     edge out 8 at 4 CTAs: products F=47 2.74 vs 2.83 ms per hop under the locality schedule; L2-resident matrices
+//     (arxiv F=40, bf16 F=128) keep 8.
 static void choose_shape(int nvec, bool hbm_regime, int* G, int* V, int* U) {
-  (void)hbm_regime;
   if (nvec > 32) { *G = 32; *V = 2; *U = 4; return; }
   if (nvec > 16) { *G = 16; *V = 2; *U = 4; return; }
-  if (nvec > 8) { *G = 16; *V = 1; *U = 8; return; }
+  if (nvec > 8) { *G = 16; *V = 1; *U = hbm_regime ? 4 : 8; return; }
   if (nvec > 4) { *G = 8; *V = 1; *U = 8; return; }
   *G = 4;
   *V = 1;

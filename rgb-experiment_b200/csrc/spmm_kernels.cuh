@@ -429,12 +429,14 @@ constexpr int SPMM_THREADS = 256;
 // Min CTAs per SM a variant is compiled for (register cap = 65536 / (256 * minb)).  ptxas is generous
 // with registers once the epilogue grew (86-93 for the main products variant -> 2 CTAs/SM, 4.16 ms instead
 // of 2.95 ms per hop); capping the variants whose in-flight gather data needs <= 32 registers at 64
-// costs no spills and restores 4 CTAs/SM.  Variants with more data in flight get proportionally more.
+// costs no spills and restores 4 CTAs/SM.  Variants with more data in flight get proportionally more; the leanest
+// (one vector, 4 edges) fit 5 CTAs/SM in 48 registers without spills (6 CTAs / 40 registers spill 16 bytes and gain
+// nothing more: 2.77 vs 2.74 ms on the products-shaped hop).
 template <int EPV, int V, int U, bool PIPE>
 constexpr int spmm_minb() {
   constexpr int raw = ((EPV > 1) ? 4 : 1) * V * U * (PIPE ? 2 : 1);   // registers holding gathered vectors
   constexpr int need = raw + V * EPV;                                  // + fp32 accumulators
-  return need <= 40 ? 4 : (need <= 56 ? 3 : (need <= 72 ? 2 : 1));
+  return need <= 24 ? 5 : (need <= 40 ? 4 : (need <= 56 ? 3 : (need <= 72 ? 2 : 1)));
 }
 
 // per-lane vector bases: lane l of the group owns vectors l, l+G, ... of the feature tile
