@@ -19,13 +19,15 @@ def main():
     ap.add_argument("--heads", type=int, default=8)
     ap.add_argument("--channels", type=int, default=8)
     ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--long-chunk", type=int, default=0)
     args = ap.parse_args()
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.synth as S
     dev = torch.device("cuda:0")
     sg = S.make_named(args.workload, device=dev, features=False)
     N, H, C = sg.num_nodes, args.heads, args.channels
-    g = P.Graph(sg.edge_index, N, P.LOOP_REMOVE_THEN_ADD)
+    g = P.Graph(sg.edge_index, N, P.LOOP_REMOVE_THEN_ADD, chunk=args.chunk or None, long_chunk=args.long_chunk or None)
     _ = g.bwd
     gen = torch.Generator(device=dev).manual_seed(0)
     xp = torch.randn(N, H * C, device=dev, generator=gen, requires_grad=True)
@@ -50,7 +52,7 @@ def main():
     print(json.dumps({"workload": args.workload, "nnz": nnz, "H": H, "C": C, "fwd_ms": round(tf / args.iters, 3),
                       "bwd_ms": round(tb / args.iters, 3), "fwd_gteps": round(nnz / (tf / args.iters) / 1e6, 2),
                       "fwd_algorithmic_GBps": round(fwd_bytes / (tf / args.iters) / 1e6, 1),
-                      "n_long_fwd": g.fwd.n_long, "n_items_fwd": g.fwd.n_items}))
+                      "n_long_fwd": g.fwd.n_long, "n_items_fwd": g.fwd.n_items, "chunk": g.fwd.chunk, "long_chunk": g.fwd.long_chunk}))
 
 
 if __name__ == "__main__":
