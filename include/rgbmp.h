@@ -267,6 +267,11 @@ int rgbmp_cluster_lpa(const rgbmp_graph_t* g, const int32_t* deg_order, int32_t 
 int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, uint32_t* W,
                                int device, void* stream);
 
+/* One pass that prepares a folded K-hop call from an unpadded input: Z0[i, 0:ld] = X[i, 0:F] zero-padded to the
+ * 16-byte aligned leading dimension ld (the teleport term) and U0[i,:] = scale[i] * Z0[i,:] (what hop 1 gathers). fp32. */
+int rgbmp_stage_rows(const float* X, int64_t ldx, const float* scale, float* Z0, float* U0, int64_t ld,
+                     int64_t n_rows, int F, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b2) peer memory for the row-partitioned multi-GPU path (one process per GPU, NVLink P2P)
  * ------------------------------------------------------------------------------------------ */

@@ -74,6 +74,7 @@ def lib():
         "rgbmp_khop": (C.c_int, [GP, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int,
                                  C.c_int, C.c_int, EP, C.c_int, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_row_scale": (C.c_int, [c_vp, c_i64, c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, C.c_int, C.c_int, c_vp]),
+        "rgbmp_stage_rows": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
         "rgbmp_appnp_host": (C.c_int, [GP, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_i64,
                                        c_vp, c_sz, C.c_int, c_vp]),
     }

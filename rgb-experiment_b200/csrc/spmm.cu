@@ -309,6 +309,17 @@ int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, 
   return 0;
 }
 
+int rgbmp_stage_rows(const float* X, int64_t ldx, const float* scale, float* Z0, float* U0, int64_t ld, int64_t n_rows, int F,
+                     int device, void* stream) {
+  if (!X || !scale || !Z0 || !U0 || n_rows < 0 || F <= 0 || ldx < F || ld < F) return fail(RGBMP_EINVAL, "rgbmp_stage_rows: bad argument");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_stage_rows: bad device");
+  if (n_rows == 0) return 0;
+  stage_rows_kernel<<<kSMs * 8, 256, 0, (cudaStream_t)stream>>>(X, ldx, scale, Z0, U0, ld, n_rows, F);
+  RGBMP_LAUNCH_CHECK("stage_rows_kernel");
+  return 0;
+}
+
 int rgbmp_appnp_host(const rgbmp_graph_t* g, const float* dinv, const float* z0_host, float* out_host, int F, int K,
                      float alpha, float* dev_z0, float* dev_ping, float* dev_pong, float* dev_out, int64_t ld, void* ws,
                      size_t ws_bytes, int device, void* stream) {

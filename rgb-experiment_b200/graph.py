@@ -43,7 +43,7 @@ DEFAULT_WINDOW = -1         # row schedule: -1 = global degree sort (fastest on 
 CLUSTER = os.environ.get("RGBMP_CLUSTER", "auto")      # auto | 0 | 1
 CLUSTER_MIN_NODES = 200_000     # auto: below this every realistic feature matrix is L2-resident anyway
 CLUSTER_MIN_DEGREE = 4.0        # auto: mean degree below which a community's slice is not re-used enough to matter
-CLUSTER_SEEDS = 1024
+CLUSTER_SEEDS = 512             # 256 / 1024 / 4096 seeds gave the same hop time (2.86 / 2.84 / 2.85 ms); fewer seeds chain faster on the host
 CLUSTER_TAUS = (0.3, 0.15, 0.05, 0.0, 0.0, 0.0)
 CLUSTER_MIN_INTRA = 0.25        # share of edges inside a group below which the graph has no community structure to use
                                 # (a uniform random graph still reaches ~0.15: every node shares a group with the neighbour it copied)

@@ -242,7 +242,26 @@ def _khop_gcn(csr: CSR, graph: Graph, x0b: torch.Tensor, K: int, transpose: bool
     return khop_raw(csr, x0b, K, val=graph.gcn_val(transpose), ep=make_epilogue(**epkw))
 
 
+def _staged(x: torch.Tensor, d: torch.Tensor):
+    """(z0 padded to an aligned row stride, u0 = D^-1/2 z0) from an UNALIGNED fp32 input in ONE kernel (instead of a zero
+    fill, a copy and a row scale): the case of every class count that is not a multiple of four (47, 10, ...)."""
+    N, F = x.shape
+    Fp = padded_width(F, x.dtype)
+    z0 = torch.empty((N, Fp), dtype=x.dtype, device=x.device)
+    u0 = torch.empty((N, Fp), dtype=x.dtype, device=x.device)
+    xc = x if x.stride(1) == 1 else x.contiguous()
+    dev = x.device
+    check(lib().rgbmp_stage_rows(ptr(xc), xc.stride(0), ptr(d), ptr(z0), ptr(u0), Fp, N, F, dev.index, stream_of(dev)), "stage_rows")
+    return z0[:, :F], u0[:, :F], Fp
+
+
 def _appnp_khop(csr: CSR, graph: Graph, x: torch.Tensor, K: int, alpha: float, transpose: bool, fold: bool):
+    _lib.require_cuda(x, "x")
+    if fold and x.dim() == 2 and x.dtype == torch.float32 and x.size(1) % 4 != 0 and x.size(0) > 0:
+        d = graph.dinv()
+        z0, u0, ld = _staged(x, d)
+        ep = make_epilogue(row_scale=d, out2_scale=d, a=1.0 - alpha, b=alpha, T=z0, ldt=ld)
+        return khop_raw(csr, u0, K, ep=ep, keep=(z0, d))
     xb, ldx = as_rows(x)
     return _khop_gcn(csr, graph, xb, K, transpose, fold, a=1.0 - alpha, b=alpha, T=xb, ldt=ldx)
 
