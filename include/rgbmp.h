@@ -169,6 +169,7 @@ typedef struct rgbmp_graph {
                                   rgbmp_col_tag; only rgbmp_spmm / rgbmp_khop accept it      */
 } rgbmp_graph_t;
 
+
 /* Fused epilogue applied to every output row i after the segmented sum s_i (all optional):
  *   s_i = acc_in ? acc_in[i,:] + s_i : s_i                          (column-blocked accumulation)
  *   v = row_scale ? (row_div ? s_i / row_scale[i] : row_scale[i]*s_i) : s_i
@@ -260,12 +261,13 @@ int rgbmp_row_scale(const void* X, int64_t ldx, const float* scale, int divide, 
  * unlabelled node takes the most frequent label among its labelled in-neighbours (ties: smallest label) once at
  * least taus[t] (host array) of its neighbours carry one, and keeps it.  label int32 [n_rows] out, every value in
  * [0, n_seeds).  Integer work, deterministic.  rgbmp_cluster_connectivity: W[a*n_groups + b] = number of CSR
- * entries of rows labelled a whose column is labelled b (uint32 [n_groups^2], zeroed inside). */
+ * entries of rows labelled a whose column is labelled b (uint32 [n_groups^2], zeroed inside), counted over every
+ * row_stride-th row (1 = exact; the host only needs relative magnitudes to order the groups). */
 size_t rgbmp_cluster_workspace_bytes(int64_t n_rows);
 int rgbmp_cluster_lpa(const rgbmp_graph_t* g, const int32_t* deg_order, int32_t n_seeds, int iters,
                       const float* taus, int32_t* label, void* ws, size_t ws_bytes, int device, void* stream);
-int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, uint32_t* W,
-                               int device, void* stream);
+int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, int row_stride,
+                               uint32_t* W, int device, void* stream);
 
 /* One pass that prepares a folded K-hop call from an unpadded input: Z0[i, 0:ld] = X[i, 0:F] zero-padded to the
  * 16-byte aligned leading dimension ld (the teleport term) and U0[i,:] = scale[i] * Z0[i,:] (what hop 1 gathers). fp32. */

@@ -7,7 +7,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librgbmp.so")
+LIB_PATH = os.environ.get("RGBMP_LIB") or os.path.join(HERE, "librgbmp.so")   # RGBMP_LIB: A/B builds (tools/)
 
 F32, BF16 = 0, 1
 EINVAL, EALIGN, ERANGE, EWORKSPACE = -1, -2, -3, -4
@@ -65,7 +65,7 @@ def lib():
         "rgbmp_row_order_grouped": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_cluster_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_cluster_lpa": (C.c_int, [GP, c_vp, c_i32, C.c_int, C.POINTER(c_f32), c_vp, c_vp, c_sz, C.c_int, c_vp]),
-        "rgbmp_cluster_connectivity": (C.c_int, [GP, c_vp, c_i32, c_vp, C.c_int, c_vp]),
+        "rgbmp_cluster_connectivity": (C.c_int, [GP, c_vp, c_i32, C.c_int, c_vp, C.c_int, c_vp]),
         "rgbmp_row_order_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_row_order": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_spmm_workspace_bytes": (c_sz, [GP, C.c_int]),

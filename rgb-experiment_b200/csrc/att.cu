@@ -358,8 +358,15 @@ __device__ __forceinline__ void fwd_range(const AttParams& p, int64_t k0, int64_
   }
 }
 
+// RGBMP_ATT_OCC (compile-time A/B of the resident-CTA targets, tools/build_variant.py; profiles/r02_att_occupancy.txt):
+// 0 = round-2 first cut; 1 (default) = one more CTA per SM for the backward kernels (GAT fwd+bwd 6.59 -> 6.20 ms,
+// SuperGAT-MX 14.6 -> 12.2 on the Reddit-shaped layer; 12-20 bytes of spill) and for the MX eval forward (3.32 -> 3.09);
+// 2 = 4 CTAs/SM for every forward variant too (the training forms spill 100-200 bytes: 2-layer GAT epoch 24.7 -> 26.1).
+#ifndef RGBMP_ATT_OCC
+#define RGBMP_ATT_OCC 1
+#endif
 template <int SC, bool TRAIN>
-constexpr int fwd_minb() { return (TRAIN || SC == SC_MX) ? 3 : 4; }
+constexpr int fwd_minb() { return RGBMP_ATT_OCC >= 2 ? 4 : (RGBMP_ATT_OCC == 1 ? (TRAIN ? 3 : 4) : ((TRAIN || SC == SC_MX) ? 3 : 4)); }
 
 __device__ __forceinline__ void fwd_init(FwdState& st) {
   st.m = -INFINITY;
@@ -677,7 +684,9 @@ __device__ __forceinline__ void bwdT_range(const AttParams& p, int64_t k0, int64
 }
 
 template <int SC>
-constexpr int bwdT_minb() { return SC == SC_MX ? 2 : 3; }
+constexpr int bwdT_minb() {
+  return RGBMP_ATT_OCC >= 1 ? (SC == SC_MX ? 3 : (SC == SC_GAT ? 4 : 3)) : (SC == SC_MX ? 2 : 3);
+}
 
 template <int SC, int G>
 __global__ void __launch_bounds__(ATT_THREADS, bwdT_minb<SC>()) att_bwdT_rows_kernel(const AttParams p) {
@@ -841,7 +850,7 @@ __device__ __forceinline__ void bwdF_range(const AttParams& p, int64_t k0, int64
 }
 
 template <int G>
-__global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_rows_kernel(const AttParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, RGBMP_ATT_OCC >= 1 ? 3 : 2) att_bwdF_rows_kernel(const AttParams p) {
   __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   const int gl = threadIdx.x % G;
   int64_t row, k0, k1;
@@ -864,7 +873,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_rows_kernel(const Att
 }
 
 template <int G>
-__global__ void __launch_bounds__(ATT_THREADS, 2) att_bwdF_long_kernel(const AttParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, RGBMP_ATT_OCC >= 1 ? 3 : 2) att_bwdF_long_kernel(const AttParams p) {
   constexpr int Q = ATT_THREADS / G;
   __shared__ __align__(16) int32_t sm_ids[ATT_THREADS];
   __shared__ float sm_acc[Q * G * 8];

@@ -48,7 +48,7 @@ template <int MODE>
 __global__ void __launch_bounds__(CL_THREADS)
 lpa_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows, int32_t S,
                 const int32_t* __restrict__ label_in, float tau, int32_t* __restrict__ label_out,
-                unsigned int* __restrict__ W, int32_t* __restrict__ changed) {
+                unsigned int* __restrict__ W, int32_t* __restrict__ changed, int row_stride) {
   extern __shared__ unsigned int hist_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int* hist = hist_all + (size_t)warp * S;
@@ -56,7 +56,8 @@ lpa_rows_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
   __syncwarp();
   const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
   int nchanged = 0;
-  for (int64_t row = (int64_t)blockIdx.x * CL_WARPS + warp; row < n_rows; row += nwarps) {
+  for (int64_t slot = (int64_t)blockIdx.x * CL_WARPS + warp; slot * row_stride < n_rows; slot += nwarps) {
+    const int64_t row = slot * row_stride;                  // connectivity may sample every row_stride-th row
     const int32_t own = label_in[row];
     if (MODE == 0 && own >= 0) {
       if (lane == 0) label_out[row] = own;
@@ -153,7 +154,7 @@ int rgbmp_cluster_lpa(const rgbmp_graph_t* g, const int32_t* deg_order, int32_t 
   RGBMP_CUDA(cudaMemsetAsync(changed, 0, sizeof(int32_t), st));
   const unsigned grid = (unsigned)(kSMs * (smem > 64 * 1024 ? 1 : 3));
   for (int t = 0; t < iters; ++t) {
-    kern<<<grid, CL_THREADS, smem, st>>>(g->rowptr, g->col, n, n_seeds, bufs[cur], taus[t], bufs[cur ^ 1], nullptr, changed);
+    kern<<<grid, CL_THREADS, smem, st>>>(g->rowptr, g->col, n, n_seeds, bufs[cur], taus[t], bufs[cur ^ 1], nullptr, changed, 1);
     RGBMP_LAUNCH_CHECK("lpa_rows_kernel");
     cur ^= 1;
   }
@@ -162,9 +163,9 @@ int rgbmp_cluster_lpa(const rgbmp_graph_t* g, const int32_t* deg_order, int32_t 
   return 0;
 }
 
-int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, uint32_t* W, int device,
-                               void* stream) {
-  if (!g || !g->rowptr || g->n_rows <= 0 || (g->nnz > 0 && !g->col) || !label || !W)
+int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int32_t n_groups, int row_stride, uint32_t* W,
+                               int device, void* stream) {
+  if (!g || !g->rowptr || g->n_rows <= 0 || (g->nnz > 0 && !g->col) || !label || !W || row_stride < 1)
     return fail(RGBMP_EINVAL, "rgbmp_cluster_connectivity: bad argument");
   if (n_groups < 1 || n_groups > 4096) return fail(RGBMP_ERANGE, "rgbmp_cluster_connectivity: n_groups must be in 1..4096");
   DeviceGuard dg(device);
@@ -175,7 +176,7 @@ int rgbmp_cluster_connectivity(const rgbmp_graph_t* g, const int32_t* label, int
   RGBMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RGBMP_CUDA(cudaMemsetAsync(W, 0, (size_t)n_groups * n_groups * sizeof(uint32_t), st));
   const unsigned grid = (unsigned)(kSMs * (smem > 64 * 1024 ? 1 : 3));
-  kern<<<grid, CL_THREADS, smem, st>>>(g->rowptr, g->col, g->n_rows, n_groups, label, 0.f, nullptr, W, nullptr);
+  kern<<<grid, CL_THREADS, smem, st>>>(g->rowptr, g->col, g->n_rows, n_groups, label, 0.f, nullptr, W, nullptr, row_stride);
   RGBMP_LAUNCH_CHECK("lpa_rows_kernel");
   return 0;
 }

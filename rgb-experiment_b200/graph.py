@@ -44,7 +44,8 @@ CLUSTER = os.environ.get("RGBMP_CLUSTER", "auto")      # auto | 0 | 1
 CLUSTER_MIN_NODES = 200_000     # auto: below this every realistic feature matrix is L2-resident anyway
 CLUSTER_MIN_DEGREE = 4.0        # auto: mean degree below which a community's slice is not re-used enough to matter
 CLUSTER_SEEDS = 512             # 256 / 1024 / 4096 seeds gave the same hop time (2.86 / 2.84 / 2.85 ms); fewer seeds chain faster on the host
-CLUSTER_TAUS = (0.3, 0.15, 0.05, 0.0, 0.0, 0.0)
+CLUSTER_TAUS = (0.3, 0.15, 0.05, 0.0, 0.0)   # the fifth round labels the last few hundred nodes; a sixth changed none
+CLUSTER_CONN_STRIDE = 4         # the connectivity matrix only orders the groups: every 4th row is sample enough
 CLUSTER_MIN_INTRA = 0.25        # share of edges inside a group below which the graph has no community structure to use
                                 # (a uniform random graph still reaches ~0.15: every node shares a group with the neighbour it copied)
 cluster_stats = {"built": 0, "used": 0, "last": None}
@@ -269,7 +270,8 @@ def locality_groups(csr: "CSR", deg_order: torch.Tensor):
         torch.cuda.synchronize()
         t1 = time.perf_counter()
     W = torch.empty((S, S), dtype=torch.int32, device=dev)
-    check(L.rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, ptr(W), dev.index, st), "cluster_connectivity")
+    check(L.rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, int(CLUSTER_CONN_STRIDE), ptr(W), dev.index, st),
+          "cluster_connectivity")
     Wh = W.cpu().numpy().astype("int64") & 0xFFFFFFFF
     if trace:
         t2 = time.perf_counter()

@@ -60,7 +60,16 @@ class Grid:
         for g in (None, self.row_group, self.col_group):
             if g is not None or self.world > 1:
                 dist.all_reduce(t, group=g)
+                # NCCL also connects lazily per ALGORITHM: the build's first all-gather (ring) after an all-reduce
+                # (tree / NVLS) paid another 2-4 s on 4 and 8 GPUs (round-2 bench lines) -- run one of each kind
+                n = dist.get_world_size(group=g)
+                full = torch.zeros(n, device=device)
+                dist.all_gather_into_tensor(full, t, group=g)
+                objs = [None] * n
+                dist.all_gather_object(objs, 0, group=g)
         torch.cuda.synchronize(device)
+        if self.world > 1:
+            dist.barrier()
 
     def feature_slice(self, F: int, align: int = 4, fp: Optional[int] = None):
         """[lo, hi) of the feature columns of feature group `fp` (default: mine).  Slices start on

@@ -59,12 +59,18 @@ def test_label_propagation_matches_the_restated_rule_exactly(case, S):
     want = lpa_restated(csr.rowptr.cpu(), csr.col.cpu(), S, taus)
     assert torch.equal(label.cpu().long(), want)
     W = torch.empty((S, S), dtype=torch.int32, device=DEV)
-    check(lib().rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, ptr(W), 0, stream_of(csr.device)), "conn")
+    check(lib().rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, 1, ptr(W), 0, stream_of(csr.device)), "conn")
     deg = csr.rowptr[1:] - csr.rowptr[:-1]
     row = torch.repeat_interleave(torch.arange(n, device=DEV), deg)
     Wo = torch.zeros(S * S, dtype=torch.int64, device=DEV).index_add_(
         0, label.long()[row] * S + label.long()[csr.col.long()], torch.ones(csr.nnz, dtype=torch.int64, device=DEV))
     assert torch.equal(W.long().view(-1), Wo)
+    # sampled form: every 3rd row only
+    check(lib().rgbmp_cluster_connectivity(C.byref(plain), ptr(label), S, 3, ptr(W), 0, stream_of(csr.device)), "conn")
+    keep = (row % 3) == 0
+    Ws = torch.zeros(S * S, dtype=torch.int64, device=DEV).index_add_(
+        0, (label.long()[row] * S + label.long()[csr.col.long()])[keep], torch.ones(int(keep.sum()), dtype=torch.int64, device=DEV))
+    assert torch.equal(W.long().view(-1), Ws)
 
 
 def test_grouped_schedule_is_sorted_by_group_then_degree_and_changes_no_result_bit(monkeypatch):
