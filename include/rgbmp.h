@@ -226,6 +226,8 @@ typedef struct rgbmp_epilogue {
  * (cold << 25) | (hot << 27), each 0 = normal, 1 = evict-first, 2 = evict-last.  Default: hot ids
  * (bit 31 set by rgbmp_col_tag) evict-last and the rest evict-first on a tagged graph, normal otherwise. */
 #define RGBMP_TUNE_POLICY    (1 << 29)
+/* rgbmp_khop: never take the one-cluster shared-memory path (below), always one SpMM launch per hop (A/B, tests) */
+#define RGBMP_TUNE_NO_CTA    (1 << 30)
 size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F);
 int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx,
                void* Y, int64_t ldy, int F, int dtype, const rgbmp_epilogue_t* ep, int tune,
@@ -245,6 +247,14 @@ int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t
                void* hops, int64_t ld_hops, int64_t hop_stride,
                int F, int dtype, int K, const rgbmp_epilogue_t* ep, int tune,
                void* ws, size_t ws_bytes, int device, void* stream);
+/* Small graphs take ONE launch of ONE thread-block cluster (16 CTAs, 8 where 16 cannot be placed) for all K hops
+ * (csrc/khop_cta.cu; hops separated by the hardware cluster barrier, the iterate stays in ping / pong, i.e. in L2): fp32,
+ * 16-byte aligned padded rows, K >= 2, F <= 16, at most 8 MB gathered per hop, n_rows <= 200,000, no peer / acc_in / skip_empty
+ * epilogue.  Same operator, same per-row summation order.  rgbmp_set_khop_cta(0 | 1) turns the path off / on process-wide
+ * (default on; environment RGBMP_KHOP_CTA=0 turns it off) and returns the previous setting; other values only query. */
+int rgbmp_set_khop_cta(int on);
+/* number of rgbmp_khop calls of this process that took the one-cluster path */
+long long rgbmp_khop_cta_calls(void);
 
 /* Device-wide knob (the one call that touches device state): size of the L2 set-aside that
  * evict-last ("persisting") lines may occupy, clamped to the device maximum; *granted = new limit. */

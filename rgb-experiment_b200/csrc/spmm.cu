@@ -5,6 +5,10 @@
 
 namespace rgbmp {
 
+int khop_cta_try(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t ldx0, void* ping, void* pong, int64_t ldp,
+                 void* out, int64_t ldo, void* hops, int64_t ld_hops, int64_t hop_stride, int F, int dtype, int K,
+                 const rgbmp_epilogue_t* ep, cudaStream_t st, int device, int* handled);   // khop_cta.cu
+
 // packed [n,F] -> pitched z0 [n,ld] and u0 = scale*z0 [n,ld]  (host entry point staging)
 __global__ void __launch_bounds__(256)
 stage_rows_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ scale, float* __restrict__ Z0,
@@ -207,6 +211,12 @@ int rgbmp_khop(const rgbmp_graph_t* g, const float* val, const void* X0, int64_t
   DeviceGuard dg(device);
   if (!dg.ok) return fail(RGBMP_EINVAL, "rgbmp_khop: bad device %d", device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(tune & RGBMP_TUNE_NO_CTA)) {     // small graphs: all K hops in one launch of one thread-block cluster
+    int handled = 0;
+    rc = khop_cta_try(g, val, X0, ldx0, ping, pong, ldp, out, ldo, hops, ld_hops, hop_stride, F, dtype, K, ep, st, device,
+                      &handled);
+    if (handled) return rc;
+  }
   const size_t esz = dtype == RGBMP_BF16 ? 2 : 4;
   rgbmp_epilogue_t e;
   if (ep) e = *ep;

@@ -7,8 +7,9 @@
 //     16-byte loads and accumulated in registers with no cross-lane traffic;
 //   * U edges are kept in flight per group (U*V independent 16-byte loads per lane) and the next
 //     U column indices are prefetched while the current features are consumed;
-//   * edges of a row are accumulated sequentially in CSR (= stable edge) order, with separate
-//     multiply and add (no FMA contraction), which reproduces PyG-CPU scatter_add_ bit for bit;
+//   * edges of a row are accumulated sequentially in CSR (= stable edge) order: unweighted sums are plain
+//     IEEE adds and reproduce PyG-CPU scatter_add_ bit for bit; weighted sums use one fused multiply-add per
+//     element (one rounding instead of two) and are held to the 1e-5 bar only;
 //   * rows longer than `chunk` edges are split into CTA-sized work items (spmm_long_kernel) whose
 //     partial sums are combined in a fixed order (spmm_combine_kernel) -- deterministic, no atomics;
 //   * the epilogue (row scale, teleport, clamp, reset rows, pre-scaled second output) is applied
