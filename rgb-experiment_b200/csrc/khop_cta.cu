@@ -6,16 +6,18 @@
 // Correct&Smooth's 50+50 hops and the PTA label propagation on the reference's own CPU-sized datasets
 // (BASELINE configs[0]; itexperiments.py:520-526, appnp_stack.py:22, pta.py:79-84) are exactly this case.
 //
-// Here ONE cluster of C = 16 (8 where 16 cannot be placed) CTAs x 1024 threads runs all K hops; the hops are separated
+// Here ONE cluster of C = 16 (8 where 16 cannot be placed) CTAs x 512 threads runs all K hops; the hops are separated
 // by the hardware cluster barrier (barrier.cluster, release / acquire: a few hundred cycles) instead of kernel
 // boundaries.  The iterate stays in the caller's ping / pong buffers, i.e. in L2.  A group of G lanes owns a row (lane l
-// its l-th 16-byte vector) and walks the slots  g, g + C*1024/G, ...  of the degree-sorted schedule; a row's epilogue
+// its l-th 16-byte vector) and walks the slots  g, g + C*512/G, ...  of the degree-sorted schedule; a row's epilogue
 // operands are requested one row ahead; rows longer than 32 edges -- a hop's critical path -- are taken by a whole warp
 // each (32/G edge slots, 4 gathers in flight per lane, fixed-order shuffle reduction).
 // Two earlier cuts, measured on B200 and dropped (profiles/r02_small_graph_latency.txt):
 //   * everything in ONE CTA's shared memory: issue-bound on its single SM, 12 us per hop -- no better than the launches;
-//   * the iterate dealt over the cluster's DISTRIBUTED shared memory and gathered with ld.shared::cluster: a remote load
-//     costs the SM ~8 cycles per LANE (requests are not coalesced), i.e. ~2 B/clk -- 8 us per hop at F=7, 46 at F=64.
+//   * the iterate dealt over the cluster's DISTRIBUTED shared memory and gathered with ld.shared::cluster: no faster than
+//     L2 (8 us per hop at F=7, 46 at F=64 -- remote shared-memory loads are served lane by lane);
+//   * a hop barrier built from one remote mbarrier arrive per CTA (one release fence per CTA instead of one per thread)
+//     in place of barrier.cluster: within noise of it (56 vs 54 us for APPNP K=10).
 // Edges of a row accumulate sequentially in stable CSR order exactly as in spmm_rows_kernel (bit-identical for rows
 // neither path splits); the epilogue is rgbmp_epilogue_t's.
 #include <stdlib.h>
@@ -23,7 +25,11 @@
 
 namespace rgbmp {
 
-constexpr int KC_THREADS = 1024;
+// 512 threads per CTA: 1,024 (64 registers, spills) measured 5-10 % slower, 256 40 % slower (profiles/r02_small_graph_latency.txt)
+#ifndef RGBMP_KC_THREADS
+#define RGBMP_KC_THREADS 512
+#endif
+constexpr int KC_THREADS = RGBMP_KC_THREADS;       // A/B: tools/build_variant.py kc1024 -DRGBMP_KC_THREADS=1024 --only khop_cta.cu
 constexpr int KC_IDS = 32;            // column ids cached per lane group (rows up to this length)
 constexpr int KC_LONG_CAP = 1024;     // rows a warp takes instead of a lane group, listed in shared memory
 constexpr double KC_MAX_GATHER_BYTES = 8e6;        // per hop: beyond this 148 SMs beat 16
@@ -480,11 +486,14 @@ int khop_cta_try(const rgbmp_graph_t* g, const float* val, const void* X0, int64
   if (ep) p.ep = *ep;
   else { p.ep = rgbmp_epilogue_t{}; p.ep.a = 1.0f; }
   const int nvec = ld / 4;
+  const int rc = nvec <= 1 ? kc_launch<1>(p, st, device) : (nvec <= 2 ? kc_launch<2>(p, st, device) : kc_launch<4>(p, st, device));
+  if (rc != 0) {               // no 8-CTA cluster can be placed on this device / partition: leave the path off for good
+    g_kc_override = 0;
+    return 0;                  // not handled: the caller runs the K-launch path
+  }
   *handled = 1;
   ++g_kc_calls;
-  if (nvec <= 1) return kc_launch<1>(p, st, device);
-  if (nvec <= 2) return kc_launch<2>(p, st, device);
-  return kc_launch<4>(p, st, device);
+  return 0;
 }
 
 }  // namespace rgbmp
