@@ -228,6 +228,11 @@ typedef struct rgbmp_epilogue {
 #define RGBMP_TUNE_POLICY    (1 << 29)
 /* rgbmp_khop: never take the one-cluster shared-memory path (below), always one SpMM launch per hop (A/B, tests) */
 #define RGBMP_TUNE_NO_CTA    (1 << 30)
+/* Fused all-gather (epilogue peer_out[]): rows of the short-row kernel reach the peers as 16-byte stores per lane
+ * (default) or as ONE bulk asynchronous copy per (row, peer) from a shared-memory image of the row (cp.async.bulk, TMA).
+ * rgbmp_set_push_bulk(0 | 1) selects process-wide (environment RGBMP_PUSH_BULK=1: bulk) and returns the previous
+ * setting; other values only query.  Same bytes in the same places either way; measured equally fast. */
+int rgbmp_set_push_bulk(int on);
 size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F);
 int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx,
                void* Y, int64_t ldy, int F, int dtype, const rgbmp_epilogue_t* ep, int tune,

@@ -64,6 +64,7 @@ def lib():
                                                  C.c_int, c_vp]),
         "rgbmp_row_order_grouped": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_sz, C.c_int, c_vp]),
         "rgbmp_set_khop_cta": (C.c_int, [C.c_int]),
+        "rgbmp_set_push_bulk": (C.c_int, [C.c_int]),
         "rgbmp_khop_cta_calls": (C.c_longlong, []),
         "rgbmp_cluster_workspace_bytes": (c_sz, [c_i64]),
         "rgbmp_cluster_lpa": (C.c_int, [GP, c_vp, c_i32, C.c_int, C.POINTER(c_f32), c_vp, c_vp, c_sz, C.c_int, c_vp]),

@@ -35,6 +35,18 @@ pack_rows_kernel(const float* __restrict__ X, int64_t ld, float* __restrict__ Y,
   }
 }
 
+// bulk (TMA) pushes of the fused all-gather: off unless RGBMP_PUSH_BULK=1 / rgbmp_set_push_bulk(1).  Measured on the
+// products-shaped APPNP (profiles/r02_push_bulk.txt): 2 GPUs 75.0 GTEPS bulk vs 76.9 stores, 4 GPUs 4x1 125.1 vs 126.4,
+// 2x2 123.7 vs 125.5 -- bit-identical results, no gain: the way a row leaves the SM is not what limits the partitioned hop.
+static int g_push_bulk = -1;
+static int push_bulk_default() {
+  if (g_push_bulk < 0) {
+    const char* e = getenv("RGBMP_PUSH_BULK");
+    g_push_bulk = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_push_bulk;
+}
+
 // choose (G, V, U) for nvec 16-byte vectors per row.  Measured on B200 with the round-2 inner loop (column ids
 // staged through shared memory, lanes beyond F issue no load; tools/sweep.py, profiles/r02_sweep.txt):
 //   * one vector per lane with 8 plain (not software-pipelined) edges in flight wins wherever a row fits 16 lanes --
@@ -81,6 +93,7 @@ static int spmm_prepare(const rgbmp_graph_t* g, const float* val, const void* X,
   p.col = g->col;
   p.val = val;
   p.row_order = g->row_order;
+  p.push_bulk = push_bulk_default();
   p.n_rows = g->n_rows;
   p.chunk = g->n_items > 0 ? g->chunk : 0;
   p.long_chunk = g->long_chunk;
@@ -182,6 +195,12 @@ extern "C" {
 size_t rgbmp_spmm_workspace_bytes(const rgbmp_graph_t* g, int F) {
   if (!g || g->n_items <= 0) return 256;
   return (size_t)g->n_items * align_up((size_t)F, 4) * sizeof(float) + 256;
+}
+
+int rgbmp_set_push_bulk(int on) {
+  const int old = push_bulk_default();
+  if (on == 0 || on == 1) g_push_bulk = on;
+  return old;
 }
 
 int rgbmp_spmm(const rgbmp_graph_t* g, const float* val, const void* X, int64_t ldx, void* Y, int64_t ldy, int F,

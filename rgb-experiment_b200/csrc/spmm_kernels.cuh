@@ -49,6 +49,9 @@ struct SpmmParams {
   // pol_hot for column ids tagged hot (bit 31 set by rgbmp_col_tag), pol_cold for the rest.  With
   // an untagged graph every row takes pol_cold.
   int pol_hot, pol_cold;
+  // fused all-gather: 1 = the short-row kernel stages each finished row in shared memory and pushes it to every peer with
+  // one bulk asynchronous copy (cp.async.bulk, TMA) instead of 16-byte st.global per lane
+  int push_bulk;
   // epilogue
   rgbmp_epilogue_t ep;
 };
@@ -380,8 +383,9 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t k0
 }
 
 // epilogue for EPV consecutive features [f, f+EPV) of row `row`
+// push = false: the caller pushes the row to the peers itself (bulk copy of the staged row); s returns what is pushed
 template <typename T, int EPV>
-__device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row, int f, float (&s)[EPV]) {
+__device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row, int f, float (&s)[EPV], bool push = true) {
   const rgbmp_epilogue_t& ep = p.ep;
   const float rs = ep.row_scale ? __ldg(ep.row_scale + row) : 1.0f;
   const bool reset = (ep.reset_when != 0) && ep.reset_mask[row];
@@ -422,8 +426,9 @@ __device__ __forceinline__ void epilogue_store(const SpmmParams& p, int64_t row,
     for (int i = 0; i < EPV; ++i) s[i] = __fmul_rn(s2, s[i]);
     if (ep.Y2) Raw<T, EPV>::store(reinterpret_cast<T*>(ep.Y2) + row * ep.ldy2 + f, s, p.stream);
   }
-  for (int q = 0; q < ep.n_peers; ++q)   // fused all-gather: push the finished row to every peer over NVLink
-    Raw<T, EPV>::store(reinterpret_cast<T*>(ep.peer_out[q]) + (ep.peer_row0 + row) * ep.ld_peer + f, s, 0);
+  if (push)
+    for (int q = 0; q < ep.n_peers; ++q)   // fused all-gather: push the finished row to every peer over NVLink
+      Raw<T, EPV>::store(reinterpret_cast<T*>(ep.peer_out[q]) + (ep.peer_row0 + row) * ep.ld_peer + f, s, 0);
 }
 
 constexpr int SPMM_THREADS = 256;
@@ -481,13 +486,38 @@ __global__ void __launch_bounds__(SPMM_THREADS, spmm_minb<EPV, V, U, PIPE>()) sp
   const IdStage stage = {sm_ids + (threadIdx.x & ~31), sm_wts + (HASW ? (threadIdx.x & ~31) : 0)};
   accumulate_range<T, EPV, G, V, U, HASW, PIPE>(p, k0, k1, xb, active, gl, stage, acc);
   if (row < 0 || (p.ep.skip_empty && k1 == k0)) return;
+  // Fused all-gather, bulk form: the group's lanes lay the finished (pre-scaled) row out in shared memory and ONE lane hands
+  // it to the TMA engine once per peer (cp.async.bulk shared -> global over NVLink): full-line writes issued off the LSU
+  // path.  Optional (rgbmp_set_push_bulk): measured no faster than 16-byte st.global per lane at 2 and 4 GPUs.
+  extern __shared__ __align__(16) unsigned char sm_push[];          // [SPMM_THREADS * V] 16-byte vectors when pushing in bulk
+  const bool bulk = (EPV > 1) && p.push_bulk && p.ep.n_peers > 0;
+  T* my_stage = reinterpret_cast<T*>(sm_push) + (size_t)(threadIdx.x / G) * (G * V * EPV);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     if (active[v]) {
       float s[EPV];
 #pragma unroll
       for (int i = 0; i < EPV; ++i) s[i] = (i & 1) ? acc[v][i / 2].y : acc[v][i / 2].x;
-      epilogue_store<T, EPV>(p, row, f0 + v * G * EPV, s);
+      epilogue_store<T, EPV>(p, row, f0 + v * G * EPV, s, !bulk);
+      if (bulk) Raw<T, EPV>::store(my_stage + (v * G + gl) * EPV, s, 0);
+    }
+  }
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // my generic-proxy writes, before the async proxy reads them
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
+    __syncwarp(gmask);
+    if (gl == 0) {
+      const int ftile = blockIdx.y * (G * V * EPV);
+      const int nv = min(G * V, (p.F - ftile + EPV - 1) / EPV);        // vectors of this tile that exist
+      const uint32_t src = (uint32_t)__cvta_generic_to_shared(my_stage);
+      const uint32_t bytes = (uint32_t)nv * 16u;
+      for (int q = 0; q < p.ep.n_peers; ++q) {
+        T* dst = reinterpret_cast<T*>(p.ep.peer_out[q]) + (p.ep.peer_row0 + row) * p.ep.ld_peer + ftile;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staged row may go once it has been read
     }
   }
 }
@@ -577,7 +607,8 @@ int launch_cfg(const SpmmParams& p, cudaStream_t st) {
   constexpr int GPB = SPMM_THREADS / G;
   if (p.n_rows > 0) {
     dim3 grid((unsigned)ceil_div(p.n_rows, GPB), ytiles);
-    spmm_rows_kernel<T, EPV, G, V, U, HASW, PIPE><<<grid, SPMM_THREADS, 0, st>>>(p);
+    const size_t push_smem = (EPV > 1 && p.push_bulk && p.ep.n_peers > 0) ? (size_t)SPMM_THREADS * V * 16 : 0;
+    spmm_rows_kernel<T, EPV, G, V, U, HASW, PIPE><<<grid, SPMM_THREADS, push_smem, st>>>(p);
     RGBMP_LAUNCH_CHECK("spmm_rows_kernel");
   }
   if (p.n_items > 0) {

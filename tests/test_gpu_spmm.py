@@ -255,3 +255,45 @@ def test_hot_tagged_gathers_do_not_change_results(case, F):
     finally:
         G_.HOT_L2_BYTES = old
         p._lib.lib().rgbmp_set_khop_cta(cta)
+
+
+@pytest.mark.parametrize("F,dtype", [(7, torch.float32), (24, torch.float32), (47, torch.float32), (64, torch.float32),
+                                     (100, torch.float32), (300, torch.float32), (128, torch.bfloat16)])
+@pytest.mark.parametrize("case", ["loops_dups", "medium"])
+def test_peer_push_epilogue_fills_every_copy_in_both_forms(case, F, dtype):
+    """Fused all-gather epilogue on one GPU: every `peer_out` buffer (here three local ones) receives rows
+    [peer_row0, peer_row0 + n) = out2_scale * epilogue(row sum), nothing else is touched, and the bulk (TMA) form of the
+    push writes the same bytes as the 16-byte stores.  (`medium` has rows for the long-row kernels, which always store.)"""
+    p = P()
+    L = p._lib.lib()
+    ei, n = CASES[case]()
+    g = p.Graph(ei.to(DEV), n, p.LOOP_ADD_REMAINING)
+    d = g.dinv()
+    x = torch.randn(n, F, generator=torch.Generator().manual_seed(F)).to(DEV).to(dtype)
+    xb, ldx = p.ops.as_rows(x)
+    ld = p.ops.padded_width(F, dtype)
+    row0, tail = 3, 2
+    tele = dict(a=0.9, b=0.1, T=xb, ldt=ldx)
+    y = p.ops.spmm_raw(g.fwd, x, None, ep=p.ops.make_epilogue(row_scale=d, **tele), keep=(xb, d))
+    want = (y.float() * d.view(-1, 1)).to(dtype)          # what the next hop gathers: one fp32 multiply, then the store's rounding
+    got = {}
+    old = L.rgbmp_set_push_bulk(1)
+    try:
+        for bulk in (1, 0):
+            L.rgbmp_set_push_bulk(bulk)
+            bufs = [torch.full((row0 + n + tail, ld), float("nan"), dtype=dtype, device=DEV) for _ in range(3)]
+            ep = p.ops.make_epilogue(row_scale=d, out2_scale=d, peers=[b.data_ptr() for b in bufs], peer_row0=row0, ld_peer=ld, **tele)
+            assert p.ops.spmm_raw(g.fwd, x, None, ep=ep, keep=(xb, d, bufs), store_local=False) is None
+            torch.cuda.synchronize()
+            for b in bufs:
+                if dtype == torch.float32:
+                    assert torch.equal(b[row0:row0 + n, :F], want)
+                else:                                     # `want` was rounded to bf16 before the scale, the kernel rounds after
+                    assert relerr(b[row0:row0 + n, :F].float(), want.float()) <= 2 ** -7
+                assert torch.isnan(b[:row0].float()).all() and torch.isnan(b[row0 + n:].float()).all()
+            got[bulk] = bufs
+    finally:
+        L.rgbmp_set_push_bulk(old)
+    for a, b in zip(got[0], got[1]):
+        # pad columns included (the long-row kernels store element by element and leave a row's pad untouched: NaN in both)
+        assert torch.equal(torch.nan_to_num(a[row0:row0 + n].float(), nan=7.0), torch.nan_to_num(b[row0:row0 + n].float(), nan=7.0))
