@@ -372,12 +372,15 @@ def case_products(args, dev, rank, world):
         grid = PT.Grid(rank, world, Pf)
         grid.warm_up(dev)                               # sub-communicator set-up (seconds) is not graph-build time
         t0 = time.perf_counter()
-        blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group)
+        flo, fhi = grid.feature_slice(F)
+        F_local = fhi - flo
+        # row blocks are runs of whole communities (nodes renamed by locality group; same operator on the renamed graph,
+        # z0 is synthetic either way): --relabel 0 keeps the id-range blocks
+        blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group,
+                            relabel=bool(args.relabel), row_bytes=F_local * 4)
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
         nnz = blk.nnz_global
-        flo, fhi = grid.feature_slice(F)
-        F_local = fhi - flo
         prop = PT.PartitionedAPPNP(blk, F_local, group=grid.row_group, mode=args.exchange)
         z0l = torch.zeros((blk.R, prop.ld), device=dev)
         z0l[: blk.hi - blk.lo, :F_local] = torch.randn(blk.hi - blk.lo, F, device=dev,
@@ -397,7 +400,7 @@ def case_products(args, dev, rank, world):
         weighted = args.exchange == "allgather"          # the push path folds D^-1/2 too
         c.hop_bytes = algorithmic_bytes_per_hop(nnz // grid.Pr, N // grid.Pr, F_local, weighted)
         par = f"{grid.Pr} row blocks x {grid.Pf} feature slices, exchange={args.exchange}"
-        sched = {"used": bool(getattr(blk.csr, "clustered", False))}
+        sched = {"used": bool(getattr(blk.csr, "clustered", False)), "community_row_blocks": blk.inv is not None}
 
         def check():
             """Rank 0 (row block 0, feature slice 0) recomputes ITS rows on its own GPU from the whole graph and the
@@ -405,7 +408,8 @@ def case_products(args, dev, rank, world):
             out = prop.run(z0l, K_HOPS, ALPHA).clone()
             res = None
             if rank == 0:
-                g1 = P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING)
+                ei_chk = sg.edge_index if blk.inv is None else blk.inv[sg.edge_index]     # the renamed graph
+                g1 = P.Graph(ei_chk, N, P.LOOP_ADD_REMAINING)
                 R_ = blk.R
                 z_full = torch.cat([torch.randn(min(N, (q + 1) * R_) - q * R_, F, device=dev,
                                                 generator=torch.Generator(device=dev).manual_seed(1 + q))
@@ -587,6 +591,8 @@ def main():
     ap.add_argument("--fold", type=int, default=1,
                     help="products: 1 (the shim layer's default): D^-1/2 (A+I) D^-1/2 applied as row scalings around an unweighted "
                          "sum (no per-edge weight stream); 0: per-edge gcn_norm weights exactly as PyG multiplies them")
+    ap.add_argument("--relabel", type=int, default=1,
+                    help="N > 1: 1 = row blocks are runs of whole locality groups (nodes renamed), 0 = id ranges")
     ap.add_argument("--feature-groups", type=int, default=0,
                     help="N>1: Pf of the Pr x Pf process grid (features split Pf ways, rows N/Pf ways); 0 = auto")
     ap.add_argument("--exchange", default="push", choices=["push", "allgather"],

@@ -144,10 +144,19 @@ class LocalBlock:
     """This rank's CSR row block + normalisation, built by the integer kernels."""
 
     def __init__(self, edge_index: torch.Tensor, N: int, loop_mode: int, rank: int, world: int, group=None,
-                 transpose_of: Optional["LocalBlock"] = None):
+                 transpose_of: Optional["LocalBlock"] = None, relabel: bool = False, row_bytes: Optional[int] = None):
         """transpose_of: build the block of the TRANSPOSED graph (rows = sources in my range, columns =
         targets) for the backward pass; it reuses the forward block's D^-1/2 (the backward of
-        D^-1/2 A D^-1/2 is D^-1/2 A^T D^-1/2 with the same degree vector, also on directed graphs)."""
+        D^-1/2 A D^-1/2 is D^-1/2 A^T D^-1/2 with the same degree vector, also on directed graphs).
+
+        relabel: rename the nodes so that a row block is a run of whole locality groups (communities) instead of a
+        run of ids: new id = position in (group rank, old id) order.  A rank then gathers mostly from its own
+        communities' slice of the iterate (tools/emulate_rank.py --by-community: the row block's hop 7-15 % faster on the
+        products-shaped graph).  The propagation is the same operator on the renamed graph: row i of every [N, F] operand
+        and result is node `perm[i]` of the caller's numbering (`perm` new -> old, `inv` old -> new; None when the
+        graph has no community structure to use).  A transposed block takes its forward block's naming.
+        row_bytes: bytes of one row of the feature slice this block will propagate (F_local * element size), if known:
+        decides between the locality-grouped and the plain degree schedule of the block (below)."""
         from . import _lib
         from ._lib import check, lib, ptr, stream_of
         from .graph import CSR, NORM_INV_SQRT, _ws
@@ -168,31 +177,45 @@ class LocalBlock:
         self.N, self.rank, self.world = N, rank, world
         self.R = rows_per_rank(N, world)
         self.lo, self.hi = row_range(N, rank, world)
+        e_src, e_dst = e_src[:nnz], e_dst[:nnz]
         # locality groups of the row schedule (graph.locality_groups): a property of the NODES of the whole graph, so
         # every rank derives them from the (replicated) edge list and gets the same answer without communication;
         # the transposed block reuses the forward block's
         from .graph import locality_groups
+        self.perm = self.inv = None
         if transpose_of is not None:
-            self.groups = transpose_of.groups
+            self.groups, self.perm, self.inv = transpose_of.groups, transpose_of.perm, transpose_of.inv
         else:
-            whole = CSR(e_dst[:nnz], e_src[:nnz], N, N, finish=False)
+            whole = CSR(e_dst, e_src, N, N, finish=False)
             self.groups = locality_groups(whole, whole.degree_order()) if N > 1 and nnz > 0 else None
             del whole
+            if relabel and self.groups is not None:
+                grp, n_groups = self.groups
+                ids = torch.arange(N, dtype=torch.int64, device=dev)
+                self.perm = torch.argsort(grp.to(torch.int64) * N + ids)          # new id -> old id (keys are unique)
+                self.inv = torch.empty_like(self.perm)
+                self.inv[self.perm] = ids                                         # old id -> new id
+                self.groups = (grp[self.perm].contiguous(), n_groups)            # group of every node under its new name
+        if self.inv is not None:
+            e_src = self.inv[e_src.long()].to(torch.int32)
+            e_dst = self.inv[e_dst.long()].to(torch.int32)
         if transpose_of is None:
-            key, other = local_edges(e_src[:nnz], e_dst[:nnz], self.lo, self.hi)
+            key, other = local_edges(e_src, e_dst, self.lo, self.hi)
         else:                                   # bucket by SOURCE: row = local source id, col = global target id
-            key, other = local_edges(e_dst[:nnz], e_src[:nnz], self.lo, self.hi)
+            key, other = local_edges(e_dst, e_src, self.lo, self.hi)
         del e_src, e_dst
+        # Row schedule of the block (tools/emulate_rank.py, profiles/r02_emulated_rank.txt): blocks whose result is ~90 MB
+        # and more keep the locality-grouped schedule and split long rows at 256 edges (a (group, -degree) order leaves
+        # long rows in the last wave: 2x1 block 1.52 ms with chunk 1024, 1.42 with 256; 4x1 0.77 vs 0.84 without groups);
+        # smaller blocks run the plain degree schedule faster (4x2: 0.425 vs 0.453 ms, 8x1: 0.374 vs 0.399, 8x2: 0.215 vs 0.234).
+        big = (self.R * row_bytes >= 90e6) if row_bytes else (self.R >= 1_000_000)
         local_groups = None
-        if self.groups is not None:
+        if self.groups is not None and big:
             grp, n_groups = self.groups
             mine = torch.zeros(self.R, dtype=torch.int32, device=dev)
             mine[: self.hi - self.lo] = grp[self.lo:self.hi]
             local_groups = (mine, n_groups)
-        # small row blocks under a grouped schedule split long rows earlier: a (group, -degree) order leaves long rows in
-        # the last wave, and on a block of < 1 M rows that tail is 10-20 % of the hop (tools/emulate_rank.py: 612 k-row
-        # block, F=47: 0.89 ms with chunk 1024, 0.77 with 256; without groups 0.84)
-        ck = (256, 2048) if (local_groups is not None and self.R < 1_000_000) else (None, None)
+        ck = (256, 2048) if local_groups is not None else (None, None)
         self.csr = CSR(key, other, self.R, self.R * world, chunk=ck[0], long_chunk=ck[1], groups=local_groups)
         self._norms(group, transpose_of)
 
@@ -206,7 +229,7 @@ class LocalBlock:
         self.N, self.rank, self.world = n_nodes, rank, world
         self.R = rows_per_rank(n_nodes, world)
         self.lo, self.hi = row_range(n_nodes, rank, world)
-        self.groups = None
+        self.groups = self.perm = self.inv = None
         rowptr, col = synth.rowgen_block(n_nodes, n_edges, self.lo, self.hi, device=device, **gen_kw)
         if self.hi - self.lo < self.R:             # pad the last block with empty rows
             rowptr = torch.cat([rowptr, rowptr[-1:].expand(self.R - (self.hi - self.lo))])

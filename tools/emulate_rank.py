@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--Pf", default="1,2")
     ap.add_argument("--F", type=int, default=47)
     ap.add_argument("--chunks", default="1024:4096", help="comma list of chunk:long_chunk")
+    ap.add_argument("--by-community", action="store_true",
+                    help="rank 0 owns the first N/Pr nodes in (locality group, id) order instead of the ids [0, N/Pr)")
     args = ap.parse_args()
     import rgb_experiment_b200 as P
     import rgb_experiment_b200.partition as PT
@@ -37,13 +39,24 @@ def main():
             res = []
             for rp in range(1):
                 lo, hi = PT.row_range(N, rp, Pr)
-                key, other = PT.local_edges(g.e_src, g.e_dst, lo, hi)
+                if args.by_community and g.groups is not None:
+                    # position of every node in (group, id) order; the block owns positions [lo, hi); columns keep their ids
+                    order = torch.argsort(g.groups[0].long() * N + torch.arange(N, device=dev), stable=True)
+                    pos = torch.empty(N, dtype=torch.int64, device=dev)
+                    pos[order] = torch.arange(N, device=dev)
+                    pd = pos[g.e_dst.long()]
+                    m = (pd >= lo) & (pd < hi)
+                    key, other = (pd[m] - lo).to(torch.int32), g.e_src[m].to(torch.int32)
+                    grp_local = g.groups[0][order[lo:hi]]
+                else:
+                    key, other = PT.local_edges(g.e_src, g.e_dst, lo, hi)
+                    grp_local = g.groups[0][lo:hi] if g.groups is not None else None
                 for use_groups, chunk, lchunk in [(ug, int(c.split(":")[0]), int(c.split(":")[1])) for c in args.chunks.split(",")
                                                   for ug in (True, False)]:
                     groups = None
                     if use_groups and g.groups is not None:
                         mine = torch.zeros(R, dtype=torch.int32, device=dev)
-                        mine[: hi - lo] = g.groups[0][lo:hi]
+                        mine[: hi - lo] = grp_local
                         groups = (mine, g.groups[1])
                     csr = CSR(key, other, R, R * Pr, chunk=chunk, long_chunk=lchunk, groups=groups)
                     x = torch.randn(R * Pr, ld, device=dev)
@@ -65,7 +78,7 @@ def main():
                     ms = e0.elapsed_time(e1) / 10
                     res.append({"rp": rp, "groups": use_groups, "chunk": f"{chunk}:{lchunk}", "ms": round(ms, 4), "n_items": csr.n_items})
                     del csr, x, out
-            print(json.dumps({"Pr": Pr, "Pf": Pf, "F_local": Fl, "rows": R, "runs": res,
+            print(json.dumps({"by_community": bool(args.by_community), "Pr": Pr, "Pf": Pf, "F_local": Fl, "rows": R, "runs": res,
                               "whole_job_gteps_if_all_ranks_like_this": round(g.nnz / max(r["ms"] for r in res if r["groups"]) / 1e6, 1)}), flush=True)
 
 
