@@ -52,3 +52,37 @@ def test_rowgen_block_propagation_matches_oracle(dtype, tol):
     z0[:, :F] = xq.to(dev)
     out = prop.run(z0, K, 0.0)[:N, :F]
     assert relerr(out.float(), ref) <= tol * K
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("relabel", [False, True])
+def test_local_block_with_community_naming_is_the_same_operator(relabel, monkeypatch):
+    """LocalBlock(relabel=True) renames the nodes by (locality group, id) before bucketing the rows: row i of every
+    operand / result is node perm[i] of the caller's numbering, inv is the inverse, and the propagation is the same
+    operator -- K hops on the block (world size 1: the whole renamed graph) equal ops.appnp on the original graph,
+    read through perm."""
+    import rgb_experiment_b200 as P
+    import rgb_experiment_b200.graph as G_
+    import rgb_experiment_b200.partition as PT
+    import rgb_experiment_b200.synth as S
+    monkeypatch.setattr(G_, "CLUSTER", "1")                # the test graph is far below the size where grouping pays
+    dev = torch.device("cuda:0")
+    sg = S.make_graph(30_000, 600_000, 8, 16, seed=5, device=dev, features=False)
+    N, F, K, alpha = sg.num_nodes, 10, 4, 0.1
+    blk = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, 0, 1, relabel=relabel)
+    x = torch.randn(N, F, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    want = P.ops.appnp(x, P.Graph(sg.edge_index, N, P.LOOP_ADD_REMAINING), K, alpha)
+    if relabel:
+        assert blk.perm is not None and torch.equal(blk.inv[blk.perm], torch.arange(N, device=dev))
+        grp = blk.groups[0].long()
+        assert bool((grp[1:] >= grp[:-1]).all())           # a row range is a run of whole groups
+        x_in, want = x[blk.perm], want[blk.perm]
+    else:
+        assert blk.perm is None and blk.inv is None
+        x_in = x
+    prop = PT.PartitionedAPPNP(blk, F)
+    z0 = torch.zeros((blk.R, prop.ld), device=dev)
+    z0[:, :F] = x_in
+    got = prop.run(z0, K, alpha)[:N, :F]
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err <= 1e-6, err
