@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--feature-groups", type=int, default=0)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--relabel", type=int, default=1, help="N > 1: row blocks = runs of whole locality groups (1) or id ranges (0)")
     ap.add_argument("--as-called", action="store_true", help="1 GPU: also time the epoch through the reference's own classes")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -77,7 +78,7 @@ def main():
 def default_args(**kw):
     """The argument set of main() as a namespace (bench.py calls run() with it)."""
     d = dict(workload="products", hidden=64, K=10, alpha=0.1, epochs=5, warmup=2, feature_groups=0, check=False,
-             as_called=False)
+             as_called=False, relabel=1)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -199,9 +200,13 @@ def run(args, rank, world, dev):
     else:
         Pf = args.feature_groups if args.feature_groups > 0 else PT.auto_feature_groups(world, C)
         grid = PT.Grid(rank, world, Pf)
-        fwd = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group)
-        bwd = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group, transpose_of=fwd)
         a, b = grid.feature_slice(C)
+        # community row blocks: the nodes are renamed by locality group, my rows are the nodes fwd.perm[lo:hi] of the dataset's
+        # numbering (features, labels and masks are read through it once, below); the transposed block takes the same naming
+        fwd = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group,
+                            relabel=bool(getattr(args, "relabel", 1)), row_bytes=(b - a) * 4)
+        bwd = PT.LocalBlock(sg.edge_index, N, P.LOOP_ADD_REMAINING, grid.rp, grid.Pr, group=grid.row_group, transpose_of=fwd,
+                            row_bytes=(b - a) * 4)
         ld = PT.DistAPPNP.slice_ld(grid, C)
         pf = PT.PartitionedAPPNP(fwd, b - a, group=grid.row_group, ld=ld)
         pb = PT.PartitionedAPPNP(bwd, b - a, group=grid.row_group, ld=ld)
@@ -217,8 +222,11 @@ def run(args, rank, world, dev):
 
     # the dense layers (and the BatchNorm statistics) see exactly my rows; only the propagation works on
     # ceil(N/Pr)-row blocks, so its input is zero-padded and its output trimmed
-    x_loc, y_loc = sg.x[lo:hi].contiguous(), y[lo:hi].contiguous()
-    m_loc = {k: m[lo:hi].contiguous() for k, m in masks.items()}
+    rows = slice(lo, hi)
+    if world > 1 and fwd.perm is not None:
+        rows = fwd.perm[lo:hi]
+    x_loc, y_loc = sg.x[rows].contiguous(), y[rows].contiguous()
+    m_loc = {k: m[rows].contiguous() for k, m in masks.items()}
     n_glob = {k: int(m.sum()) for k, m in masks.items()}
     params = [p for p in model.parameters()]
 
@@ -297,7 +305,7 @@ def run(args, rank, world, dev):
         if world > 1:
             dist.all_reduce(flat)
         flat1 = torch.cat([p.grad.reshape(-1) for p in m1.parameters()])
-        e_logit = float((lp - lp1[lo:hi]).abs().max() / lp1.abs().max())
+        e_logit = float((lp - lp1[rows]).abs().max() / lp1.abs().max())
         e_grad = float((flat - flat1).abs().max() / flat1.abs().max())
         stat = torch.tensor([e_logit, e_grad], device=dev)
         if world > 1:
