@@ -94,6 +94,26 @@ def auto_feature_groups(world: int, F: int) -> int:
     return 1
 
 
+def community_naming(group: torch.Tensor, N: int):
+    """Rename the nodes so that equal-sized row blocks are runs of whole locality groups: new id = position in
+    (group rank, old id) order.  Returns (perm, inv) int64 [N]: perm[new] = old, inv[old] = new.  Plain torch: the same
+    answer on every rank from the same `group`, on any device."""
+    ids = torch.arange(N, dtype=torch.int64, device=group.device)
+    perm = torch.argsort(group.to(torch.int64) * N + ids)             # keys are unique: no tie order to worry about
+    inv = torch.empty_like(perm)
+    inv[perm] = ids
+    return perm, inv
+
+
+def block_keeps_groups(R: int, row_bytes: Optional[int]) -> bool:
+    """Schedule of a row block (tools/emulate_rank.py, profiles/r02_emulated_rank.txt): blocks whose result is ~90 MB and more
+    keep the locality-grouped schedule, with long rows split at 256 edges (a (group, -degree) order leaves long rows in the
+    last wave: 2x1 block 1.52 ms with chunk 1024, 1.42 with 256; 4x1 0.77 vs 0.84 without groups); smaller blocks run the
+    plain degree schedule faster (4x2: 0.425 vs 0.453 ms, 8x1: 0.374 vs 0.399, 8x2: 0.215 vs 0.234).  row_bytes unknown:
+    a million rows decide."""
+    return (R * row_bytes >= 90e6) if row_bytes else (R >= 1_000_000)
+
+
 def local_edges(e_src: torch.Tensor, e_dst: torch.Tensor, lo: int, hi: int):
     """Edges whose TARGET falls in [lo, hi), order preserved: (local target id, global source id).
     Because the filter keeps the relative order, the stable CSR of the bucket equals the matching
@@ -191,10 +211,7 @@ class LocalBlock:
             del whole
             if relabel and self.groups is not None:
                 grp, n_groups = self.groups
-                ids = torch.arange(N, dtype=torch.int64, device=dev)
-                self.perm = torch.argsort(grp.to(torch.int64) * N + ids)          # new id -> old id (keys are unique)
-                self.inv = torch.empty_like(self.perm)
-                self.inv[self.perm] = ids                                         # old id -> new id
+                self.perm, self.inv = community_naming(grp, N)                    # new id -> old id, old id -> new id
                 self.groups = (grp[self.perm].contiguous(), n_groups)            # group of every node under its new name
         if self.inv is not None:
             e_src = self.inv[e_src.long()].to(torch.int32)
@@ -204,13 +221,8 @@ class LocalBlock:
         else:                                   # bucket by SOURCE: row = local source id, col = global target id
             key, other = local_edges(e_dst, e_src, self.lo, self.hi)
         del e_src, e_dst
-        # Row schedule of the block (tools/emulate_rank.py, profiles/r02_emulated_rank.txt): blocks whose result is ~90 MB
-        # and more keep the locality-grouped schedule and split long rows at 256 edges (a (group, -degree) order leaves
-        # long rows in the last wave: 2x1 block 1.52 ms with chunk 1024, 1.42 with 256; 4x1 0.77 vs 0.84 without groups);
-        # smaller blocks run the plain degree schedule faster (4x2: 0.425 vs 0.453 ms, 8x1: 0.374 vs 0.399, 8x2: 0.215 vs 0.234).
-        big = (self.R * row_bytes >= 90e6) if row_bytes else (self.R >= 1_000_000)
         local_groups = None
-        if self.groups is not None and big:
+        if self.groups is not None and block_keeps_groups(self.R, row_bytes):
             grp, n_groups = self.groups
             mine = torch.zeros(self.R, dtype=torch.int32, device=dev)
             mine[: self.hi - self.lo] = grp[self.lo:self.hi]

@@ -60,3 +60,34 @@ def test_graph_cache_key_distinguishes_what_it_must():
     assert k != _graph_key(ei.t().contiguous().t(), 4, 2, False)          # other storage / strides
     ei[0, 0] = 1                                                           # in-place edit bumps _version
     assert k != _graph_key(ei, 4, 2, False)
+
+
+def test_community_naming_makes_row_blocks_runs_of_whole_groups_and_keeps_the_operator():
+    """partition.community_naming: perm / inv are inverse permutations, the groups are non-decreasing under the new
+    names (equal-sized row blocks are runs of whole groups), ids keep their order inside a group, and propagating on
+    the renamed edge list is the same operator read through perm (checked with the CPU oracle)."""
+    import rgb_experiment_b200.partition as PT
+    from oracle import pyg_restated as R
+    gen = torch.Generator().manual_seed(0)
+    N, S = 97, 5
+    group = torch.randint(S, (N,), generator=gen, dtype=torch.int32)
+    perm, inv = PT.community_naming(group, N)
+    ids = torch.arange(N)
+    assert torch.equal(inv[perm], ids) and torch.equal(perm[inv], ids)
+    g_new = group[perm].long()
+    assert bool((g_new[1:] >= g_new[:-1]).all())
+    same = g_new[1:] == g_new[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())
+    ei = torch.randint(N, (2, 400), generator=gen)
+    x = torch.randn(N, 6, generator=gen, dtype=torch.float64)
+    z = R.appnp_propagate(x, ei, 3, 0.1)
+    z_new = R.appnp_propagate(x[perm], inv[ei], 3, 0.1)
+    assert torch.allclose(z_new, z[perm], rtol=0, atol=1e-12)
+
+
+def test_block_schedule_rule():
+    import rgb_experiment_b200.partition as PT
+    assert PT.block_keeps_groups(1_224_515, 47 * 4) and PT.block_keeps_groups(1_224_515, 24 * 4)      # 2x1, 2x2
+    assert PT.block_keeps_groups(612_258, 47 * 4)                                                      # 4x1
+    assert not PT.block_keeps_groups(612_258, 24 * 4) and not PT.block_keeps_groups(306_129, 47 * 4)   # 4x2, 8x1
+    assert PT.block_keeps_groups(1_000_000, None) and not PT.block_keeps_groups(999_999, None)

@@ -81,6 +81,29 @@ def main():
                 fin(P.ops.label_propagation(gn, x.detach(), 3, 0.8, reset_mask=m, reset_val=x.detach()))
                 w = torch.rand(g.nnz, device=dev, generator=gen, requires_grad=True)
                 back(P.ops.propagate_weighted(x, w, g), x, w)
+                if F <= 16:                                    # the same K-hop families on the K-launch path (cluster path off)
+                    L_ = P._lib.lib()
+                    old = L_.rgbmp_set_khop_cta(0)
+                    try:
+                        fin(P.ops.appnp(x.detach(), g, 3, 0.1))
+                        fin(P.ops.label_propagation(gn, x.detach(), 3, 0.8, clamp=(-1.0, 1.0)))
+                    finally:
+                        L_.rgbmp_set_khop_cta(old)
+                # fused all-gather epilogue into two local "peer" copies, as stores and as bulk (TMA) copies
+                d = g.dinv()
+                xb, ldx = P.ops.as_rows(x.detach())
+                ldp = P.ops.padded_width(F, dt)
+                for bulk in (0, 1):
+                    oldb = P._lib.lib().rgbmp_set_push_bulk(bulk)
+                    try:
+                        bufs = [torch.zeros((n + 4, ldp), dtype=dt, device=dev) for _ in range(2)]
+                        ep = P.ops.make_epilogue(row_scale=d, out2_scale=d, a=0.9, b=0.1, T=xb, ldt=ldx,
+                                                 peers=[b_.data_ptr() for b_ in bufs], peer_row0=2, ld_peer=ldp)
+                        P.ops.spmm_raw(g.fwd, x.detach(), None, ep=ep, keep=(xb, d, bufs), store_local=False)
+                        for b_ in bufs:
+                            fin(b_)
+                    finally:
+                        P._lib.lib().rgbmp_set_push_bulk(oldb)
             else:
                 fin(P.ops.spmm_raw(g.fwd, x, None))
             n_calls += 8
