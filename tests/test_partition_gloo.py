@@ -217,3 +217,59 @@ def test_dist_appnp_autograd_on_a_grid_matches_single_process():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert all(ret.get(r) is True for r in range(world))
+
+
+def _relabel_worker(rank, world, port, ret):
+    """Community row blocks: every rank renames the nodes from the same (replicated) group vector, buckets the renamed
+    edges, propagates its block; the gathered result read back through inv equals the single-process oracle on the
+    ORIGINAL graph (same operator under another node naming; rounding differs only by the order of a row's edges,
+    which the renaming keeps)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import rgb_experiment_b200.partition as PT
+        from oracle import pyg_restated as R
+        torch.manual_seed(0)
+        N, F, K, alpha, S = 101, 6, 5, 0.1, 7
+        ei = torch.randint(N, (2, 900))
+        group = torch.randint(S, (N,), dtype=torch.int32)
+        z0 = torch.randn(N, F)
+        perm, inv = PT.community_naming(group, N)
+        ed, w = R.gcn_norm(inv[ei], None, N, dtype=torch.float32)        # the renamed graph: edge order unchanged
+        Rr = PT.rows_per_rank(N, world)
+        lo, hi = PT.row_range(N, rank, world)
+        g_new = group[perm]
+        if rank + 1 < world and hi < N:                                 # a block boundary never splits ids out of group order
+            assert int(g_new[hi - 1]) <= int(g_new[hi])
+        key, src = PT.local_edges(ed[0], ed[1], lo, hi)
+        wl = w[(ed[1] >= lo) & (ed[1] < hi)]
+
+        def spmm(x_full, z0_local, a, b):
+            out = torch.zeros(Rr, x_full.size(1)).index_add_(0, key.long(), wl.view(-1, 1) * x_full[src.long()])
+            return out * a + b * z0_local
+
+        z0_local = torch.zeros(Rr, F)
+        z0_local[: hi - lo] = z0[perm[lo:hi]]                           # my rows are the nodes perm[lo:hi] of the caller
+        drv = PT.PartitionedPropagator(N, rank, world, spmm)
+        out_local = drv.run(z0_local, K, 1 - alpha, alpha)
+        full = torch.empty(Rr * world, F)
+        dist.all_gather_into_tensor(full, out_local)
+        ref = R.appnp_propagate(z0, ei, K, alpha)
+        ret[rank] = bool(torch.equal(full[:N][inv], ref))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_community_row_blocks_match_the_single_process_oracle():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_relabel_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert ret.get(0) is True and ret.get(1) is True
