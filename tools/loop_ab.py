@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""NEEDS profiles/r02_loop_kernel.patch applied (`git apply profiles/r02_loop_kernel.patch`, rebuild): the looping kernel
-was measured slower and is not in the tree; this is the tool that produced profiles/r02_loop_kernel_ab.txt.
+"""HISTORICAL: the tool that produced profiles/r02_loop_kernel_ab.txt.  The looping kernel it times was measured slower and
+is not in the tree (kernel side kept as profiles/r02_loop_kernel.patch; the `row_sched` descriptor field, its builder call in
+graph.py and `rgbmp_set_rows_per_group` in the header / _lib.py went with it), so this script does not run as is.
 A/B of the looping short-row SpMM kernel (spmm_rows_loop_kernel) against the one-row-per-group kernel:
 ms per hop of the K-hop families and per launch of the plain aggregations, for rows-per-group 0 (old kernel), 1, 2, ...
     python tools/loop_ab.py [--workloads products,arxiv,reddit] [--rpg 0,1,4,8,16,32]"""
